@@ -1,0 +1,168 @@
+/*
+ * unsloth_b200 -- C ABI of the B200 (sm_100a) fused-kernel QLoRA fine-tuning hot path.
+ *
+ * The reference (unslothai/unsloth @ 015bdef) has no C ABI on this path: its boundary is a set
+ * of Python callables (unsloth/kernels/__init__.py:15-62) whose bodies launch Triton kernels,
+ * cuBLAS GEMMs and three bitsandbytes C symbols bound through ctypes
+ * (unsloth/kernels/utils.py:273-284).  This header declares what a ctypes binding for the path
+ * binds instead; each entry point cites the reference function whose device work it replaces.
+ *
+ * Conventions: the caller owns every buffer (outputs pre-allocated by the
+ * caller, e.g. torch.empty); all pointers are device pointers unless stated; functions never
+ * allocate, never synchronise and only enqueue work on `stream` (pass the CURRENT stream, not one
+ * cached at import); no thread-local or global mutable state, so forward and autograd's backward
+ * thread may call concurrently.  Return value: 0 (UB200_OK), a negative UB200_ERR_* code, or a
+ * positive cudaError_t from the launch.  dtype codes: UB200_F32 / UB200_F16 / UB200_BF16.
+ * Row strides are in ELEMENTS.
+ */
+#ifndef UNSLOTH_B200_H_
+#define UNSLOTH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define UB200_OK 0
+#define UB200_ERR_BAD_ARG (-1)
+#define UB200_ERR_UNSUPPORTED (-2)
+#define UB200_ERR_NO_DRIVER (-3) /* cuTensorMapEncodeTiled could not be resolved */
+#define UB200_ERR_TMAP (-4)      /* tensor-map encoding rejected the operand */
+
+#define UB200_F32 0
+#define UB200_F16 1
+#define UB200_BF16 2
+
+#define UB200_ACT_SWIGLU 0
+#define UB200_ACT_GEGLU_APPROX 1
+#define UB200_ACT_GEGLU_EXACT 2
+
+#define UB200_GEMM_MAX_SEGMENTS 8
+
+/* ABI version of this header (bumped on any signature change). */
+int ub200_abi_version(void);
+
+/* ---- RMSNorm --------------------------------------------------------------------------------
+ * fast_rms_layernorm / Fast_RMS_Layernorm (unsloth/kernels/rms_layernorm.py:162-255).
+ * fwd: Y = (X * rsqrt(mean(X^2) + eps)).to(W.dtype) * W   (gemma: fp32, * (1 + W)); r[T] fp32.
+ * bwd: dX only (weights frozen); dX may alias dY (the reference's in-place contract).       */
+int ub200_rms_layernorm_fwd(const void* X, int64_t x_row_stride, const void* W, int w_dtype,
+                            void* Y, int64_t y_row_stride, float* r, int64_t n_rows, int n_cols,
+                            float eps, int gemma, int dtype, cudaStream_t stream);
+int ub200_rms_layernorm_bwd(const void* dY, int64_t dy_row_stride, const void* X,
+                            int64_t x_row_stride, const void* W, int w_dtype, const float* r,
+                            void* dX, int64_t dx_row_stride, int64_t n_rows, int n_cols, int gemma,
+                            int dtype, cudaStream_t stream);
+
+/* ---- RoPE -----------------------------------------------------------------------------------
+ * fast_rope_embedding (unsloth/kernels/rope_embedding.py:265-280): Fast_RoPE_Embedding (:169-261)
+ * and Fast_RoPE_Embedding_QK (:283-399) as ONE strided in-place kernel over Q and K.
+ * Element (b,h,s,d) of Q is at Q + b*q_batch_stride + h*q_head_stride + s*q_seq_stride + d.
+ * K may be NULL.  indices: int32 [batch*seqlen] row of cos/sin per token, or NULL (row = s).
+ * backward != 0 negates sin.  compute_dtype: dtype in which products/sums are rounded (table
+ * dtype for the no-index form, promoted dtype for the QK form).                              */
+int ub200_rope_qk(void* Q, int64_t q_batch_stride, int64_t q_head_stride, int64_t q_seq_stride,
+                  void* K, int64_t k_batch_stride, int64_t k_head_stride, int64_t k_seq_stride,
+                  const void* cos, int64_t cos_row_stride, const void* sin, int64_t sin_row_stride,
+                  const int32_t* indices, int batch, int seqlen, int n_heads_q, int n_heads_k,
+                  int head_dim, int backward, int dtype, int table_dtype, int compute_dtype,
+                  cudaStream_t stream);
+
+/* ---- SwiGLU / GEGLU -------------------------------------------------------------------------
+ * swiglu_fg_kernel / swiglu_DWf_DW_dfg_kernel (unsloth/kernels/swiglu.py:50-64, 112-125),
+ * geglu_{approx,exact}_{forward,backward}_kernel (unsloth/kernels/geglu.py).
+ * fwd: h = act(e).to(dtype) * g.  bwd (in place): DW <- h, e <- df = DW*f, g <- de.           */
+int ub200_glu_fwd(int act, const void* e, const void* g, void* h, int64_t n, int dtype,
+                  cudaStream_t stream);
+int ub200_glu_bwd(int act, void* DW, void* e, void* g, int64_t n, int dtype, cudaStream_t stream);
+
+/* ---- cross entropy on materialised logits ---------------------------------------------------
+ * Fast_CrossEntropyLoss (unsloth/kernels/cross_entropy_loss.py:288-418); one path for any
+ * vocabulary size (the reference splits at 65,536).  labels int64, -100 = ignore.
+ * fwd writes loss[T], logsumexp[T] (fp32).  bwd overwrites logits with
+ * dloss[row*dloss_stride] * d loss / d logits.  softcap / scale == 0 disables them.          */
+int ub200_cross_entropy_fwd(const void* logits, int64_t row_stride, const int64_t* labels,
+                            float* loss, float* lse, int64_t n_rows, int vocab, float softcap,
+                            float scale, int dtype, cudaStream_t stream);
+int ub200_cross_entropy_bwd(void* logits, int64_t row_stride, const float* lse,
+                            const int64_t* labels, const float* dloss, int64_t dloss_stride,
+                            int64_t n_rows, int vocab, float softcap, float scale, int dtype,
+                            cudaStream_t stream);
+
+/* ---- NF4 -------------------------------------------------------------------------------------
+ * fast_dequantize (unsloth/kernels/utils.py:567-679).  One launch for both stages of the
+ * double-quantised format: absmax = code2[absmax_q[i]] * absmax2[i / blocksize2] + *offset,
+ * out[2j] = NF4[packed[j] >> 4] * absmax[2j / blocksize], out[2j+1] = NF4[packed[j] & 15] * ...
+ * `offset` is a DEVICE scalar (may be NULL = 0).  n = number of weights.                       */
+int ub200_dequantize_nf4(const uint8_t* packed, const uint8_t* absmax_q, const float* code2,
+                         const float* absmax2, const float* offset, void* out, int64_t n,
+                         int blocksize, int blocksize2, int out_dtype, cudaStream_t stream);
+/* Blockwise NF4 quantiser (blocksize 64): packed[n/2], absmax[n/64] fp32 (first level only).  */
+int ub200_quantize_nf4(const void* W, int dtype, uint8_t* packed, float* absmax, int64_t n,
+                       int blocksize, cudaStream_t stream);
+/* The bitsandbytes symbols the reference binds (unsloth/kernels/utils.py:273-284, call sites
+ * :650-675) with their exact signatures: void return, errors surface at the next sync.        */
+void cdequantize_blockwise_fp32(float* code, unsigned char* A, float* absmax, float* out,
+                                int blocksize, const int n, cudaStream_t stream);
+#ifdef __CUDACC__
+void cdequantize_blockwise_bf16_nf4(float* code, unsigned char* A, float* absmax,
+                                    __nv_bfloat16* out, int blocksize, const int n,
+                                    cudaStream_t stream);
+void cdequantize_blockwise_fp16_nf4(float* code, unsigned char* A, float* absmax, __half* out,
+                                    int blocksize, const int n, cudaStream_t stream);
+#else
+void cdequantize_blockwise_bf16_nf4(float* code, unsigned char* A, float* absmax, void* out,
+                                    int blocksize, const int n, cudaStream_t stream);
+void cdequantize_blockwise_fp16_nf4(float* code, unsigned char* A, float* absmax, void* out,
+                                    int blocksize, const int n, cudaStream_t stream);
+#endif
+
+/* ---- tcgen05 GEMM ---------------------------------------------------------------------------
+ * The primitive under matmul_lora (unsloth/kernels/utils.py:1128-1170) and the dX / dA / dB
+ * GEMMs of LoRA_MLP / LoRA_QKV / LoRA_W.backward (unsloth/kernels/fast_lora.py:116-229,
+ * 432-540, 617-650):
+ *      C[M,N] = alpha * sum_s A_s . B_s^T   (+ C if accumulate)
+ * Every segment contributes K_s to the reduction; all accumulate in fp32 in TMEM.
+ *   a_mn_major == 0: A_s is row-major [M, K_s] (lda);  != 0: A_s is row-major [K_s, M].
+ *   b_mn_major == 0: B_s is row-major [N, K_s] (ldb);  != 0: B_s is row-major [K_s, N].
+ * Operands bf16 (or fp16), 16-byte aligned, ld multiple of 8.  C: bf16/fp16/fp32, ldc elements.
+ * split_k > 1 needs `workspace` of ub200_gemm_workspace_bytes(); reduction order is fixed
+ * (deterministic).  block_n: 0 = auto, or 64 / 128 / 256.                                      */
+typedef struct {
+  const void* a;
+  int64_t lda;
+  const void* b;
+  int64_t ldb;
+  int64_t k;
+} ub200_gemm_segment;
+int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
+               int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype, float alpha,
+               int accumulate, int split_k, void* workspace, int block_n, cudaStream_t stream);
+int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* bytes);
+
+/* ---- small helpers of the LoRA path ---------------------------------------------------------
+ * Writes the whole [dst_rows, dst_cols] destination: the block at (dst_row_off, dst_col_off)
+ * receives scale * src (src is [rows, cols]; transposed first when transpose != 0, i.e. the
+ * block is then [cols, rows]) and everything else is zero.  This is A.to(dtype) /
+ * (s*B).to(dtype) of matmul_lora (unsloth/kernels/utils.py:1163-1167), zero-padded to the
+ * 64-wide K block of the GEMM and placed at the adapter's slot of a shared rank block.        */
+int ub200_cast_pad_2d(const void* src, int src_dtype, int64_t src_ld, int rows, int cols,
+                      void* dst, int dst_dtype, int64_t dst_ld, int dst_rows, int dst_cols,
+                      int dst_row_off, int dst_col_off, float scale, int transpose,
+                      cudaStream_t stream);
+
+/* Flat AdamW over the LoRA parameter bucket (fp32 p, g, m, v of length n), decoupled weight
+ * decay; bias corrections are passed in (1 - beta^t).  grad_scale multiplies g first.          */
+int ub200_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float bias_corr1,
+                     float bias_corr2, float grad_scale, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNSLOTH_B200_H_ */

@@ -1,0 +1,167 @@
+"""Pins oracle/restate.py (the CPU oracle) against the committed golden vectors that
+oracle/make_golden.py produced by executing the REFERENCE's own Triton kernels
+(TRITON_INTERPRET=1, fp32).  Tolerance: 1e-5 (north_star fp32 gate)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+
+TOL = dict(rtol=1e-5, atol=1e-5)
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def close(a, b, **kw):
+    kw = {**TOL, **kw}
+    torch.testing.assert_close(a, T(b) if not torch.is_tensor(b) else b, **kw)
+
+
+@pytest.mark.parametrize("name", ["rms_llama_512", "rms_llama_odd", "rms_gemma_256",
+                                  "rms_selftest_512", "rms_selftest_1024"])
+def test_rmsnorm(golden, name):
+    g = golden(name)
+    X, W, dY = T(g["X"]), T(g["W"]), T(g["dY"])
+    gemma = bool(g["gemma"])
+    Y, r = R.rms_layernorm_fwd(X, W, float(g["eps"]), gemma)
+    close(Y, g["Y"])
+    dX = R.rms_layernorm_bwd(dY, X, W, r, gemma)
+    close(dX, g["dX"], atol=2e-5)
+    if "Y_hf" in g:  # reference self-test bar (kernels/rms_layernorm.py:326): amax<=0.05
+        assert (dX - T(g["dX_hf"])).abs().max() <= 0.05
+        close(Y, g["Y_hf"])
+
+
+def test_rope_noindex(golden):
+    g = golden("rope_noindex")
+    Q, K, cos, sin = (T(g[k]) for k in ("Q", "K", "cos", "sin"))
+    # the reference transposes to [B,S,H,D] before its kernel (rope_embedding.py:276)
+    Qo = R.rope_noindex(Q.transpose(1, 2), cos, sin).transpose(1, 2)
+    Ko = R.rope_noindex(K.transpose(1, 2), cos, sin).transpose(1, 2)
+    close(Qo, g["Qo"]); close(Ko, g["Ko"])
+    gQ = R.rope_noindex(T(g["dQ"]).transpose(1, 2), cos, sin, backward=True).transpose(1, 2)
+    gK = R.rope_noindex(T(g["dK"]).transpose(1, 2), cos, sin, backward=True).transpose(1, 2)
+    close(gQ, g["gQ"]); close(gK, g["gK"])
+
+
+def test_rope_index(golden):
+    g = golden("rope_index")
+    Q, K, cos, sin, idx = (T(g[k]) for k in ("Q", "K", "cos", "sin", "idx"))
+    Qo, Ko = R.rope_qk(Q, K, cos, sin, idx)
+    close(Qo, g["Qo"]); close(Ko, g["Ko"])
+    gQ, gK = R.rope_qk(T(g["dQ"]), T(g["dK"]), cos, sin, idx, backward=True)
+    close(gQ, g["gQ"]); close(gK, g["gK"])
+    # no indices == arange positions
+    Q2, K2 = R.rope_qk(Q, K, cos, sin, None)
+    Q3, K3 = R.rope_qk(Q, K, cos, sin, torch.arange(Q.shape[2]).repeat(Q.shape[0]))
+    close(Q2, Q3); close(K2, K3)
+
+
+@pytest.mark.parametrize("name", ["ce_v1000", "ce_v70000_chunked", "ce_softcap30", "ce_scale"])
+def test_cross_entropy(golden, name):
+    g = golden(name)
+    logits, labels = T(g["logits"]), T(g["labels"])
+    loss, dlogits = R.fast_cross_entropy_loss(logits, labels, float(g["softcap"]), float(g["scale"]))
+    close(loss, g["loss"])
+    close(dlogits, g["dlogits"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name,fwd,bwd", [
+    ("swiglu", R.swiglu_fwd, R.swiglu_bwd),
+    ("geglu_approx", R.geglu_approx_fwd, R.geglu_approx_bwd),
+    ("geglu_exact", R.geglu_exact_fwd, R.geglu_exact_bwd)])
+def test_glu(golden, name, fwd, bwd):
+    g = golden(name)
+    e, up, DW = T(g["e"]), T(g["g"]), T(g["DW"])
+    close(fwd(e, up), g["h"])
+    h, df, de = bwd(DW, e.reshape(DW.shape), up.reshape(DW.shape))
+    close(h, g["bh"]); close(df, g["bdf"]); close(de, g["bde"], atol=2e-5)
+
+
+@pytest.mark.parametrize("act", ["swiglu", "geglu_approx"])
+def test_lora_mlp(golden, act):
+    g = golden("lora_mlp_" + act)
+    t = {k: T(v) for k, v in g.items()}
+    s = float(g["s"])
+    gate = (t["gW"], None, t["gA"], t["gB"], s)
+    up = (t["uW"], None, t["uA"], t["uB"], s)
+    down = (t["dW"], None, t["dA"], t["dB"], s)
+    out, e, gg = R.lora_mlp_fwd(t["X"], gate, up, down, act)
+    close(out, g["out"])
+    dX, (dgA, dgB), (duA, duB), (ddA, ddB) = R.lora_mlp_bwd(t["dY"], t["X"], e, gg, gate, up, down, act)
+    close(dX, g["dX"])
+    for mine, key in ((dgA, "d_gA"), (dgB, "d_gB"), (duA, "d_uA"), (duB, "d_uB"),
+                      (ddA, "d_dA"), (ddB, "d_dB")):
+        close(mine, g[key], atol=2e-5)
+
+
+def test_lora_qkv(golden):
+    g = golden("lora_qkv")
+    t = {k: T(v) for k, v in g.items()}
+    s = float(g["s"])
+    q = (t["qW"], None, t["qA"], t["qB"], s)
+    k = (t["kW"], None, t["kA"], t["kB"], s)
+    v = (t["vW"], None, t["vA"], t["vB"], s)
+    Q, K, V = R.lora_qkv_fwd(t["X"], q, k, v)
+    close(Q, g["Q"]); close(K, g["K"]); close(V, g["V"])
+    dX, gq, gk, gv = R.lora_qkv_bwd(t["dQ"], t["dK"], t["dV"], t["X"], q, k, v)
+    close(dX, g["dX"])
+    for (a, b), n in ((gq, "q"), (gk, "k"), (gv, "v")):
+        close(a, g["d_%sA" % n], atol=2e-5); close(b, g["d_%sB" % n], atol=2e-5)
+
+
+def test_lora_w(golden):
+    g = golden("lora_w")
+    t = {k: T(v) for k, v in g.items()}
+    o = (t["oW"], None, t["oA"], t["oB"], float(g["s"]))
+    close(R.lora_w_fwd(t["X"], o), g["O"])
+    dX, (dA, dB) = R.lora_w_bwd(t["dY"], t["X"], o)
+    close(dX, g["dX"]); close(dA, g["d_oA"], atol=2e-5); close(dB, g["d_oB"], atol=2e-5)
+
+
+def test_nf4_roundtrip():
+    """NF4 double-quant restatement (parity unpinned): self-consistency properties."""
+    torch.manual_seed(3407)
+    W = torch.randn(128, 256) * 0.02
+    packed, qs = R.quantize_nf4(W.to(torch.bfloat16))
+    assert packed.shape == (128 * 256 // 2, 1) and packed.dtype == torch.uint8
+    assert qs.absmax.dtype == torch.uint8 and qs.absmax.numel() == 128 * 256 // 64
+    assert qs.state2.code.numel() == 256 and qs.state2.absmax.numel() == 2
+    D = R.dequantize_nf4(packed, qs)
+    assert D.shape == W.shape and D.dtype == torch.bfloat16
+    # quantisation error bounded by half the largest NF4 gap times the block absmax
+    blk = W.reshape(-1, 64)
+    err = (D.float().reshape(-1, 64) - blk).abs().amax(1) / blk.abs().amax(1)
+    assert err.max() < 0.2
+    # idempotence: re-quantising the dequantised weight reproduces the same codes
+    packed2, _ = R.quantize_nf4(D)
+    assert (packed2 == packed).float().mean() > 0.99
+    # transposed-call contract (kernels/utils.py:678-679)
+    assert R.fast_dequantize(packed.t(), qs).shape == (256, 128)
+    assert R.fast_dequantize(W, None) is W
+
+
+def test_fused_linear_ce_matches_logits_path():
+    torch.manual_seed(0)
+    B, S, H, V = 2, 7, 32, 101
+    hidden = torch.randn(B, S, H)
+    Wlm = torch.randn(V, H) * 0.1
+    labels = torch.randint(0, V, (B, S)); labels[0, 3] = -100
+    loss, dH = R.fused_linear_cross_entropy(hidden, Wlm, labels)
+    h = hidden.clone().requires_grad_()
+    logits = h @ Wlm.t()
+    ref = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1),
+                                            ignore_index=-100)
+    ref.backward()
+    torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dH, h.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_packing_label_vector(golden):
+    """tests/utils/test_packing.py:1489-1525 of the reference: boundary-masked labels."""
+    g = golden("packing_labels")
+    from unsloth_b200.packing import mask_packed_boundary_labels
+    out = mask_packed_boundary_labels(T(g["labels"])[None].clone(), T(g["packed_seq_lengths"]))
+    assert out[0].tolist() == g["expected"].tolist()

@@ -1,0 +1,192 @@
+// Cross entropy on materialised logits: forward (loss + logsumexp) and in-place backward.
+//
+// Replaces the reference's Triton kernels
+//   unsloth/kernels/cross_entropy_loss.py:35-111  (_cross_entropy_forward)
+//   unsloth/kernels/cross_entropy_loss.py:114-199 (_chunked_cross_entropy_forward + the three
+//                                                  torch launches at :368-370)
+//   unsloth/kernels/cross_entropy_loss.py:202-285 (_cross_entropy_backward)
+// The reference needs a separate "chunked" path for vocabularies above 65,536 (Llama-3's
+// 128,256 included) because a Triton program holds the whole row; here ONE CTA streams a
+// row of any length once with an online (max, sum-exp) pair per thread, so there is a
+// single path and no host-side logsumexp combine.
+//
+// HBM-bound.  Algorithmic bytes per row: fwd V*b (+16), bwd 2*V*b.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace ub {
+
+__device__ __forceinline__ float ce_transform(float x, float softcap, float scale) {
+  if (scale != 0.f) x = scale * x;
+  if (softcap != 0.f) x = softcap * tanhf(x / softcap);
+  return x;
+}
+
+// online logsumexp state merge
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float nm = fmaxf(m, m2);
+  if (nm == -CUDART_INF_F) { m = nm; s = 0.f; return; }
+  s = s * expf(m - nm) + s2 * expf(m2 - nm);
+  m = nm;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) ce_fwd_kernel(
+    const T* __restrict__ logits, int64_t row_stride, const int64_t* __restrict__ labels,
+    float* __restrict__ loss, float* __restrict__ lse_out, int64_t n_rows, int vocab,
+    float softcap, float scale, int vec_ok) {
+  constexpr int V = DT<T>::VEC;
+  __shared__ float sm_m[32], sm_s[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const T* x = logits + row * row_stride;
+    float m = -CUDART_INF_F, s = 0.f;
+    if (vec_ok) {
+      const int nvec = vocab / V;
+      for (int i = tid; i < nvec; i += blockDim.x) {
+        float v[V];
+        load_vec_cs<T>(x + (int64_t)i * V, v);
+        float lm = -CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < V; ++k) { v[k] = ce_transform(v[k], softcap, scale); lm = fmaxf(lm, v[k]); }
+        const float nm = fmaxf(m, lm);
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc += expf(v[k] - nm);
+        s = s * expf(m - nm) + acc;
+        m = nm;
+      }
+      for (int i = nvec * V + tid; i < vocab; i += blockDim.x) {
+        const float v = ce_transform(DT<T>::to_f(x[i]), softcap, scale);
+        lse_merge(m, s, v, 1.f);
+      }
+    } else {
+      for (int i = tid; i < vocab; i += blockDim.x) {
+        const float v = ce_transform(DT<T>::to_f(x[i]), softcap, scale);
+        lse_merge(m, s, v, 1.f);
+      }
+    }
+    // warp then block merge
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, m2, s2);
+    }
+    __syncthreads();
+    if (lane == 0) { sm_m[warp] = m; sm_s[warp] = s; }
+    __syncthreads();
+    if (warp == 0) {
+      m = lane < nw ? sm_m[lane] : -CUDART_INF_F;
+      s = lane < nw ? sm_s[lane] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge(m, s, m2, s2);
+      }
+      if (lane == 0) {
+        const float lse = m + logf(s);
+        lse_out[row] = lse;
+        const int64_t lab = labels[row];
+        float l = 0.f;
+        if (lab != -100) {
+          const float xl = ce_transform(DT<T>::to_f(x[lab]), softcap, scale);
+          l = lse - xl;
+        }
+        loss[row] = l;
+      }
+    }
+  }
+}
+
+// grid: (row, column-chunk).  In place: logits <- dloss * d(loss)/d(logits)
+template <typename T>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(
+    T* logits, int64_t row_stride, const float* __restrict__ lse, const int64_t* __restrict__ labels,
+    const float* __restrict__ dloss, int64_t dloss_stride, int vocab, float softcap, float scale,
+    int vec_ok, int cols_per_block) {
+  constexpr int V = DT<T>::VEC;
+  const int64_t row = blockIdx.x;
+  const int c0 = blockIdx.y * cols_per_block;
+  const int c1 = min(vocab, c0 + cols_per_block);
+  T* x = logits + row * row_stride;
+  const int64_t lab = labels[row];
+  const float dl = (lab != -100) ? dloss[row * dloss_stride] : 0.f;
+  const float l = lse[row];
+  auto grad = [&](float xv, int col) {
+    if (scale != 0.f) xv = xv * scale;
+    float partial = xv;
+    if (softcap != 0.f) { partial = tanhf(xv / softcap); xv = softcap * partial; }
+    float y = expf(xv - l);
+    if (col == lab) y -= 1.0f;
+    if (scale != 0.f) y *= scale;
+    if (softcap != 0.f) y *= (1.0f - partial * partial);
+    return dl * y;
+  };
+  if (vec_ok) {
+    for (int c = c0 + threadIdx.x * V; c < c1; c += blockDim.x * V) {
+      float v[V];
+      load_vec_cs<T>(x + c, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = grad(v[k], c + k);
+      store_vec<T>(x + c, v);
+    }
+  } else {
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
+      x[c] = DT<T>::from_f(grad(DT<T>::to_f(x[c]), c));
+  }
+}
+
+}  // namespace ub
+
+extern "C" int ub200_cross_entropy_fwd(const void* logits, int64_t row_stride,
+                                       const int64_t* labels, float* loss, float* lse,
+                                       int64_t n_rows, int vocab, float softcap, float scale,
+                                       int dtype, cudaStream_t stream) {
+  using namespace ub;
+  if (n_rows <= 0) return UB200_OK;
+  const int V = dtype == UB200_F32 ? 4 : 8;
+  const int esz = dtype_size(dtype);
+  const int vec_ok = (row_stride % V == 0) && (((uintptr_t)logits) % 16 == 0);
+  (void)esz;
+  const int threads = vocab >= 32768 ? 1024 : (vocab >= 4096 ? 512 : 128);
+  int64_t g = (int64_t)UB_SM_COUNT * 4;
+  const int grid = (int)(n_rows < g ? n_rows : g);
+#define GO(T)                                                                                  \
+  ce_fwd_kernel<T><<<grid, threads, 0, stream>>>((const T*)logits, row_stride, labels, loss, lse, \
+                                                 n_rows, vocab, softcap, scale, vec_ok)
+  if (dtype == UB200_BF16) { GO(__nv_bfloat16); }
+  else if (dtype == UB200_F16) { GO(__half); }
+  else if (dtype == UB200_F32) { GO(float); }
+  else return UB200_ERR_BAD_ARG;
+#undef GO
+  UB_RETURN_LAST();
+}
+
+extern "C" int ub200_cross_entropy_bwd(void* logits, int64_t row_stride, const float* lse,
+                                       const int64_t* labels, const float* dloss,
+                                       int64_t dloss_stride, int64_t n_rows, int vocab,
+                                       float softcap, float scale, int dtype,
+                                       cudaStream_t stream) {
+  using namespace ub;
+  if (n_rows <= 0) return UB200_OK;
+  if (n_rows > 2147483647LL) return UB200_ERR_UNSUPPORTED;
+  const int V = dtype == UB200_F32 ? 4 : 8;
+  const int vec_ok = (row_stride % V == 0) && (vocab % V == 0) && (((uintptr_t)logits) % 16 == 0);
+  const int cols_per_block = 256 * V * 4;  // 4 vectors per thread
+  const int chunks = (vocab + cols_per_block - 1) / cols_per_block;
+  if (chunks > 65535) return UB200_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)n_rows, (unsigned)chunks);
+#define GO(T)                                                                                  \
+  ce_bwd_kernel<T><<<grid, 256, 0, stream>>>((T*)logits, row_stride, lse, labels, dloss,          \
+                                             dloss_stride, vocab, softcap, scale, vec_ok,          \
+                                             cols_per_block)
+  if (dtype == UB200_BF16) { GO(__nv_bfloat16); }
+  else if (dtype == UB200_F16) { GO(__half); }
+  else if (dtype == UB200_F32) { GO(float); }
+  else return UB200_ERR_BAD_ARG;
+#undef GO
+  UB_RETURN_LAST();
+}

@@ -1,0 +1,591 @@
+// Multi-segment bf16/fp16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//     C[M,N] (+)= alpha * sum_s  A_s[M,K_s] . B_s[N,K_s]^T
+//
+// This is the primitive under the LoRA projections of the reference:
+//   unsloth/kernels/utils.py:1128-1170  matmul_lora:  X @ W.T  + (X @ A.T) @ (s B.T)
+//   unsloth/kernels/fast_lora.py:172-204, 476-517, 639-647   dX and dA/dB GEMMs
+// where the reference issues one cuBLAS call per term and rounds the running result to bf16
+// between terms.  Here every term is a K-SEGMENT of one launch: the dense base GEMM, the
+// rank-r LoRA update (as one extra K block) and -- for dX -- the sum over projections all
+// accumulate in the same fp32 TMEM accumulator and are rounded once.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) -> smem ring, mbarrier tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees stages
+//   warps 2..5  epilogue: tcgen05.ld accumulator -> registers -> alpha/beta -> global
+//   accumulators are double buffered in TMEM so the epilogue of tile i overlaps the
+//   main loop of tile i+1.
+// Operand layouts: each operand may be K-major (row-major [MN, K]) or MN-major (row-major
+// [K, MN]); MN-major is what makes dX (= dY @ W with W stored [out,in]) and the dA/dB
+// reductions over tokens (X^T @ G) run without any transpose pass.
+//
+// Roofline: tensor-bound; flops = 2*M*N*sum(K_s).
+#include <cuda.h>
+#include <dlfcn.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ub {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;           // 64 x 2 B = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_SEGS = UB200_GEMM_MAX_SEGMENTS;
+constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+
+struct SegParams {
+  int k_blocks;      // ceil(K_s / 64)
+};
+
+struct Params {
+  CUtensorMap tmap_a[MAX_SEGS];
+  CUtensorMap tmap_b[MAX_SEGS];
+  int seg_kblocks[MAX_SEGS];
+  int n_segs;
+  int M, N;
+  int a_mn, b_mn;        // operand majors (uniform over segments)
+  int m_tiles, n_tiles;
+  int split_k;           // >= 1
+  void* C;               // output (or fp32 workspace when split_k > 1)
+  int64_t ldc;
+  int64_t split_stride;  // elements between split slices of the workspace
+  int c_dtype;           // UB200_F32 / F16 / BF16
+  int accumulate;        // C = alpha*acc + C
+  float alpha;
+  int ab_fp16;           // operands are fp16 instead of bf16
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// The loaded registers are passed through the wait as in/out operands so that no use of
+// them can be scheduled ahead of tcgen05.wait::ld.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout; 128B swizzle everywhere)
+//   K-major  tile: rows of 64 elements (128 B); 8-row groups 1024 B apart        -> SBO=1024
+//   MN-major tile: [64 k-rows x 64 mn] boxes of 8 KB; 8-k-row groups 1024 B apart -> SBO=1024,
+//                  successive 64-wide MN atoms one box (8192 B) apart            -> LBO=8192
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn, int fp16) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // D format: F32
+  d |= (fp16 ? 0u : 1u) << 7;         // A format: BF16 (1) / F16 (0)
+  d |= (fp16 ? 0u : 1u) << 10;        // B format
+  d |= (uint32_t)(a_mn & 1) << 15;    // A major: 0 = K, 1 = MN
+  d |= (uint32_t)(b_mn & 1) << 16;    // B major
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);  // power of 2
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ Params p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8u * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int total_kb = 0;
+  for (int s = 0; s < p.n_segs; ++s) total_kb += p.seg_kblocks[s];
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_work = num_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_segs; ++s) { prefetch_tmap(&p.tmap_a[s]); prefetch_tmap(&p.tmap_b[s]); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // split-K range helper: k-blocks [kb0, kb1) of the concatenated segment list
+  auto work_range = [&](int w, int& tile, int& kb0, int& kb1) {
+    tile = w % num_tiles;
+    const int sp = w / num_tiles;
+    const int per = (total_kb + p.split_k - 1) / p.split_k;
+    kb0 = sp * per;
+    kb1 = min(total_kb, kb0 + per);
+  };
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    // m fastest: the CTAs running concurrently share the same B (weight) tiles in L2
+    m_blk = tile % p.m_tiles;
+    n_blk = tile / p.m_tiles;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer ===================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int tile, kb0, kb1, m_blk, n_blk;
+        work_range(w, tile, kb0, kb1);
+        tile_coords(tile, m_blk, n_blk);
+        int seg = 0, seg_start = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          while (kb >= seg_start + p.seg_kblocks[seg]) { seg_start += p.seg_kblocks[seg]; ++seg; }
+          const int k0 = (kb - seg_start) * BLOCK_K;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &p.tmap_a[seg], full_bar(stage), k0, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * 8192u, &p.tmap_a[seg], full_bar(stage), m_blk * BLOCK_M + j * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &p.tmap_b[seg], full_bar(stage), k0, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * 8192u, &p.tmap_b[seg], full_bar(stage), n_blk * BLOCK_N + j * 64, k0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, p.a_mn, p.b_mn, p.ab_fp16);
+      // per-UMMA_K advance of the descriptor start address (in 16-byte units)
+      const uint32_t a_adv = p.a_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
+      const uint32_t b_adv = p.b_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int tile, kb0, kb1;
+        work_range(w, tile, kb0, kb1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = make_smem_desc(sa, a_lbo, 1024u);
+          const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));              // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue =======================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      int tile, kb0, kb1, m_blk, n_blk;
+      work_range(w, tile, kb0, kb1);
+      tile_coords(tile, m_blk, n_blk);
+      const int sp = w / num_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool has_k = kb1 > kb0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        const int col0 = n_blk * BLOCK_N + c;
+        if (col0 >= p.N) break;                   // warp-uniform
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
+        tmem_ld32(taddr, r);
+        tmem_ld_wait(r);
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * p.alpha : 0.f;
+          const bool full = (col0 + 32 <= p.N);
+          if (p.c_dtype == UB200_F32) {
+            float* cptr = reinterpret_cast<float*>(p.C) + (int64_t)sp * p.split_stride +
+                          (int64_t)row * p.ldc + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(cptr + i);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(cptr + i) = o;
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i)
+                cptr[i] = p.accumulate ? cptr[i] + v[i] : v[i];
+            }
+          } else {
+            // 16-bit output (bf16 / fp16)
+            uint16_t* cptr = reinterpret_cast<uint16_t*>(p.C) + (int64_t)row * p.ldc + col0;
+            const bool bf = p.c_dtype == UB200_BF16;
+            if (full && ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 o;
+                if (p.accumulate) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(cptr + i);
+                  const uint16_t* oh = reinterpret_cast<const uint16_t*>(&old);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    v[i + j] += bf ? __bfloat162float(__ushort_as_bfloat16(oh[j]))
+                                   : __half2float(__ushort_as_half(oh[j]));
+                }
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (bf) {
+                    __nv_bfloat162 t = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                    ow[j] = *reinterpret_cast<uint32_t*>(&t);
+                  } else {
+                    __half2 t = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                    ow[j] = *reinterpret_cast<uint32_t*>(&t);
+                  }
+                }
+                *reinterpret_cast<uint4*>(cptr + i) = o;
+              }
+            } else {
+              for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
+                float val = v[i];
+                if (p.accumulate)
+                  val += bf ? __bfloat162float(__ushort_as_bfloat16(cptr[i]))
+                            : __half2float(__ushort_as_half(cptr[i]));
+                cptr[i] = bf ? __bfloat16_as_ushort(__float2bfloat16_rn(val))
+                             : __half_as_ushort(__float2half_rn(val));
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// sum the fp32 split-K slices; optional 16-bit output
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws,
+                                                            int64_t split_stride, int splits,
+                                                            void* __restrict__ out, int64_t ldo,
+                                                            int out_dtype, int accumulate, int M,
+                                                            int N, int64_t ld_ws) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / N, c = i - r * N;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(int64_t)s * split_stride + r * ld_ws + c];
+    const int64_t o = r * ldo + c;
+    if (out_dtype == UB200_F32) {
+      float* p = reinterpret_cast<float*>(out);
+      p[o] = accumulate ? p[o] + acc : acc;
+    } else if (out_dtype == UB200_BF16) {
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(out);
+      p[o] = __float2bfloat16_rn(accumulate ? __bfloat162float(p[o]) + acc : acc);
+    } else {
+      __half* p = reinterpret_cast<__half*>(out);
+      p[o] = __float2half_rn(accumulate ? __half2float(p[o]) + acc : acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// operand stored row-major [rows, cols] with leading dimension ld (elements);
+// box = [box_rows, 64 cols], 128B swizzle, OOB -> 0.
+static int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                     int box_rows, int fp16) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return UB200_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return UB200_ERR_BAD_ARG;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? UB200_OK : UB200_ERR_TMAP;
+}
+
+template <int BLOCK_N>
+static int launch(const Params& p, int grid, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  gemm_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  return UB200_OK;
+}
+
+}  // namespace gemm
+}  // namespace ub
+
+extern "C" int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* bytes) {
+  if (!bytes) return UB200_ERR_BAD_ARG;
+  *bytes = split_k > 1 ? (int64_t)split_k * M * N * 4 : 0;
+  return UB200_OK;
+}
+
+extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
+                          int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype,
+                          float alpha, int accumulate, int split_k, void* workspace,
+                          int block_n, cudaStream_t stream) {
+  using namespace ub;
+  using namespace ub::gemm;
+  if (M <= 0 || N <= 0) return UB200_OK;
+  if (n_segs < 1 || n_segs > MAX_SEGS || !segs) return UB200_ERR_BAD_ARG;
+  if (ab_dtype != UB200_BF16 && ab_dtype != UB200_F16) return UB200_ERR_BAD_ARG;
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && !workspace) return UB200_ERR_BAD_ARG;
+  int bn = block_n;
+  if (bn == 0) bn = (N >= 256 || N > 128) ? 256 : (N > 64 ? 128 : 64);
+  if (bn != 256 && bn != 128 && bn != 64) return UB200_ERR_BAD_ARG;
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_segs = n_segs;
+  p.M = M;
+  p.N = N;
+  p.a_mn = a_mn_major ? 1 : 0;
+  p.b_mn = b_mn_major ? 1 : 0;
+  p.ab_fp16 = ab_dtype == UB200_F16;
+  p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = (N + bn - 1) / bn;
+  int total_kb = 0;
+  for (int s = 0; s < n_segs; ++s) {
+    const ub200_gemm_segment& g = segs[s];
+    if (g.k <= 0) return UB200_ERR_BAD_ARG;
+    p.seg_kblocks[s] = (int)((g.k + BLOCK_K - 1) / BLOCK_K);
+    total_kb += p.seg_kblocks[s];
+    int rc;
+    if (!p.a_mn) rc = make_tmap(&p.tmap_a[s], g.a, M, g.k, g.lda, BLOCK_M, p.ab_fp16);
+    else         rc = make_tmap(&p.tmap_a[s], g.a, g.k, M, g.lda, 64, p.ab_fp16);
+    if (rc) return rc;
+    if (!p.b_mn) rc = make_tmap(&p.tmap_b[s], g.b, N, g.k, g.ldb, bn, p.ab_fp16);
+    else         rc = make_tmap(&p.tmap_b[s], g.b, g.k, N, g.ldb, 64, p.ab_fp16);
+    if (rc) return rc;
+  }
+  if (split_k > total_kb) split_k = total_kb;
+  p.split_k = split_k;
+  p.alpha = alpha;
+  if (split_k > 1) {
+    p.C = workspace;
+    p.ldc = N;
+    p.split_stride = (int64_t)M * N;
+    p.c_dtype = UB200_F32;
+    p.accumulate = 0;
+  } else {
+    p.C = C;
+    p.ldc = ldc;
+    p.split_stride = 0;
+    p.c_dtype = c_dtype;
+    p.accumulate = accumulate;
+  }
+  const int num_work = p.m_tiles * p.n_tiles * split_k;
+  const int grid = num_work < UB_SM_COUNT ? num_work : UB_SM_COUNT;
+  int rc;
+  if (bn == 256) rc = launch<256>(p, grid, stream);
+  else if (bn == 128) rc = launch<128>(p, grid, stream);
+  else rc = launch<64>(p, grid, stream);
+  if (rc) return rc;
+  if (split_k > 1) {
+    const int64_t total = (int64_t)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > UB_SM_COUNT * 8) blocks = UB_SM_COUNT * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>((const float*)workspace, (int64_t)M * N,
+                                                     split_k, C, ldc, c_dtype, accumulate, M, N, N);
+  }
+  UB_RETURN_LAST();
+}

@@ -1,0 +1,137 @@
+// SwiGLU / GEGLU (tanh and erf) elementwise forward and in-place backward.
+//
+// Replaces the reference's Triton kernels
+//   unsloth/kernels/swiglu.py:27-47, 67-109      (_fg_kernel, _DWf_DW_dfg_kernel)
+//   unsloth/kernels/geglu.py:142-167, 188-244    (tanh approximation, Gemma / Gemma-2)
+//   unsloth/kernels/geglu.py:31-53, 74-123       (exact erf form)
+// HBM-bound streaming: 16-byte loads/stores, grid-stride, int64 indexing throughout.
+// Algorithmic bytes per element: fwd 3*b (e,g -> h), bwd 6*b (DW,e,g -> h,df,de in place).
+// Rounding points mirror the reference (f rounded to the tensor dtype before *g, all
+// products rounded to the tensor dtype; de evaluated in fp32) -- SURVEY.md section 9.
+#include "common.cuh"
+
+namespace ub {
+
+enum { ACT_SWIGLU = 0, ACT_GEGLU_APPROX = 1, ACT_GEGLU_EXACT = 2 };
+
+// returns f(e) (fp32, before rounding) and df/de
+template <int ACT>
+__device__ __forceinline__ void act_eval(float e, float& f, float& dfde) {
+  if (ACT == ACT_SWIGLU) {
+    const float se = 1.0f / (1.0f + expf(-e));
+    f = e * se;
+    dfde = se * (1.0f + e * (1.0f - se));
+  } else if (ACT == ACT_GEGLU_APPROX) {
+    const float s = 0.7978845608028654f;
+    const float a = s * e;
+    const float b = a * 0.044715f * e * e;
+    const float T = 1.0f + tanhf(a + b);
+    const float T2 = 0.5f * T;
+    const float Q2 = -T2 * (T - 2.0f) * (a + 3.0f * b);
+    f = T2 * e;
+    dfde = T2 + Q2;
+  } else {
+    const float fp = 0.5f * (erff(0.70710678118654752f * e) + 1.0f);
+    f = fp * e;
+    dfde = fp + 0.3989422804014327f * e * expf(-0.5f * e * e);
+  }
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ e,
+                                                      const T* __restrict__ g,
+                                                      T* __restrict__ h, int64_t n_vec) {
+  constexpr int V = DT<T>::VEC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float ev[V], gv[V], o[V];
+    load_vec_cs<T>(e + i * V, ev);
+    load_vec_cs<T>(g + i * V, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float f, d;
+      act_eval<ACT>(ev[k], f, d);
+      o[k] = DT<T>::rnd(f) * gv[k];
+    }
+    store_vec<T>(h + i * V, o);
+  }
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) glu_bwd_kernel(T* DW, T* e, T* g, int64_t n_vec) {
+  constexpr int V = DT<T>::VEC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float dw[V], ev[V], gv[V], oh[V], odf[V], ode[V];
+    load_vec_cs<T>(DW + i * V, dw);
+    load_vec_cs<T>(e + i * V, ev);
+    load_vec_cs<T>(g + i * V, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float f, d;
+      act_eval<ACT>(ev[k], f, d);
+      const float fr = DT<T>::rnd(f);
+      oh[k] = fr * gv[k];                    // h  = f * g
+      odf[k] = dw[k] * fr;                   // df = DW * f
+      const float dg = DT<T>::rnd(dw[k] * gv[k]);  // dg = DW * g (tensor dtype)
+      ode[k] = dg * d;                       // de = dg.float() * df/de
+    }
+    store_vec<T>(DW + i * V, oh);
+    store_vec<T>(e + i * V, odf);
+    store_vec<T>(g + i * V, ode);
+  }
+}
+
+static inline int ew_grid(int64_t n_vec, int threads) {
+  int64_t b = (n_vec + threads - 1) / threads;
+  int64_t cap = (int64_t)UB_SM_COUNT * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace ub
+
+extern "C" int ub200_glu_fwd(int act, const void* e, const void* g, void* h, int64_t n,
+                             int dtype, cudaStream_t stream) {
+  using namespace ub;
+  if (n <= 0) return UB200_OK;
+  const int V = dtype == UB200_F32 ? 4 : 8;
+  if (n % V) return UB200_ERR_BAD_ARG;
+  const int64_t nv = n / V;
+  const int grid = ew_grid(nv, 256);
+#define GO(T, A) glu_fwd_kernel<T, A><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv)
+#define GOA(T)                                                  \
+  if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
+  else if (act == ACT_GEGLU_APPROX) GO(T, ACT_GEGLU_APPROX);    \
+  else if (act == ACT_GEGLU_EXACT) GO(T, ACT_GEGLU_EXACT);      \
+  else return UB200_ERR_BAD_ARG
+  if (dtype == UB200_BF16) { GOA(__nv_bfloat16); }
+  else if (dtype == UB200_F16) { GOA(__half); }
+  else if (dtype == UB200_F32) { GOA(float); }
+  else return UB200_ERR_BAD_ARG;
+#undef GO
+#undef GOA
+  UB_RETURN_LAST();
+}
+
+extern "C" int ub200_glu_bwd(int act, void* DW, void* e, void* g, int64_t n, int dtype,
+                             cudaStream_t stream) {
+  using namespace ub;
+  if (n <= 0) return UB200_OK;
+  const int V = dtype == UB200_F32 ? 4 : 8;
+  if (n % V) return UB200_ERR_BAD_ARG;
+  const int64_t nv = n / V;
+  const int grid = ew_grid(nv, 256);
+#define GO(T, A) glu_bwd_kernel<T, A><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv)
+#define GOA(T)                                                  \
+  if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
+  else if (act == ACT_GEGLU_APPROX) GO(T, ACT_GEGLU_APPROX);    \
+  else if (act == ACT_GEGLU_EXACT) GO(T, ACT_GEGLU_EXACT);      \
+  else return UB200_ERR_BAD_ARG
+  if (dtype == UB200_BF16) { GOA(__nv_bfloat16); }
+  else if (dtype == UB200_F16) { GOA(__half); }
+  else if (dtype == UB200_F32) { GOA(float); }
+  else return UB200_ERR_BAD_ARG;
+#undef GO
+#undef GOA
+  UB_RETURN_LAST();
+}

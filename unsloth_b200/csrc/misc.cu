@@ -1,0 +1,100 @@
+// Small helpers of the LoRA path: dtype cast with zero padding (+ optional transpose), and a
+// flat AdamW over the contiguous LoRA parameter bucket.
+//
+//  * ub200_cast_pad_2d replaces the per-call `A.to(dtype)`, `B.to(dtype)` casts and the
+//    `alpha = s` scaling of unsloth/kernels/utils.py:1163-1167 and fast_lora.py:138-153; the
+//    padding brings the rank dimension up to the 64-wide K block of the tcgen05 GEMM.
+//  * ub200_adamw_flat: the reference leaves the optimiser to torch (AdamW over 448 LoRA
+//    tensors); here the LoRA parameters live in ONE flat fp32 bucket (shared with the DDP
+//    all-reduce) so the update is a single streaming launch.  HBM-bound: 28 B / parameter.
+#include "common.cuh"
+
+namespace ub {
+
+__global__ void __launch_bounds__(256) cast_pad_kernel(const void* __restrict__ src, int sdt,
+                                                       int64_t sld, int rows, int cols,
+                                                       void* __restrict__ dst, int ddt, int64_t dld,
+                                                       int drows, int dcols, int roff,
+                                                       int coff, float scale, int transpose) {
+  const int64_t total = (int64_t)drows * dcols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int dr = (int)(i / dcols), dc = (int)(i - (int64_t)dr * dcols);
+    const int lr = dr - roff, lc = dc - coff;   // position inside the placed block
+    const int sr = transpose ? lc : lr, sc = transpose ? lr : lc;
+    float v = 0.f;
+    if (sr >= 0 && sc >= 0 && sr < rows && sc < cols) v = scale * load_as_f(src, sdt, (int64_t)sr * sld + sc);
+    const int64_t o = (int64_t)dr * dld + dc;
+    if (ddt == UB200_BF16) reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
+    else if (ddt == UB200_F16) reinterpret_cast<__half*>(dst)[o] = __float2half_rn(v);
+    else reinterpret_cast<float*>(dst)[o] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    int64_t n4, int64_t n, float lr, float b1,
+                                                    float b2, float eps, float wd, float bc1,
+                                                    float bc2, float gs) {
+  const float step = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= gs;
+    pp *= (1.0f - lr * wd);
+    mm = b1 * mm + (1.0f - b1) * gg;
+    vv = b2 * vv + (1.0f - b2) * gg * gg;
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    pp -= step * (mm / denom);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    const float4 G = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 M = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  // tail
+  const int64_t t0 = n4 * 4;
+  for (int64_t i = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    upd(p[i], g[i], m[i], v[i]);
+}
+
+}  // namespace ub
+
+extern "C" int ub200_abi_version(void) { return 1; }
+
+extern "C" int ub200_cast_pad_2d(const void* src, int src_dtype, int64_t src_ld, int rows, int cols,
+                                 void* dst, int dst_dtype, int64_t dst_ld, int dst_rows,
+                                 int dst_cols, int dst_row_off, int dst_col_off, float scale,
+                                 int transpose, cudaStream_t stream) {
+  using namespace ub;
+  if (dst_rows <= 0 || dst_cols <= 0) return UB200_OK;
+  const int64_t total = (int64_t)dst_rows * dst_cols;
+  int64_t b = (total + 255) / 256;
+  if (b > UB_SM_COUNT * 8) b = UB_SM_COUNT * 8;
+  cast_pad_kernel<<<(int)b, 256, 0, stream>>>(src, src_dtype, src_ld, rows, cols, dst, dst_dtype,
+                                              dst_ld, dst_rows, dst_cols, dst_row_off, dst_col_off, scale,
+                                              transpose);
+  UB_RETURN_LAST();
+}
+
+extern "C" int ub200_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay,
+                                float bias_corr1, float bias_corr2, float grad_scale,
+                                cudaStream_t stream) {
+  using namespace ub;
+  if (n <= 0) return UB200_OK;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                         reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const int64_t n4 = aligned ? n / 4 : 0;
+  int64_t b = ((n4 > 0 ? n4 : n) + 255) / 256;
+  if (b > UB_SM_COUNT * 8) b = UB_SM_COUNT * 8;
+  adamw_kernel<<<(int)b, 256, 0, stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay,
+                                           bias_corr1, bias_corr2, grad_scale);
+  UB_RETURN_LAST();
+}

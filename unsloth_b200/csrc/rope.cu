@@ -1,0 +1,116 @@
+// Rotary position embedding, in place, Q and K in ONE launch, forward and backward.
+//
+// Replaces the reference's Triton kernels
+//   unsloth/kernels/rope_embedding.py:104-166 (_rope_embedding, no position ids)
+//   unsloth/kernels/rope_embedding.py:23-98   (_rope_embedding_QK, strided + indices)
+// Both forms are one strided kernel here: element (b, h, s, d) lives at
+//   base + b*batch_stride + h*head_stride + s*seq_stride + d.
+// The no-index form on the contiguous [B,S,H*D] projection buffer is just
+// (batch_stride, head_stride, seq_stride) = (S*H*D, D, H*D); no clone, no host sync
+// (the reference synchronises the stream per layer when DEVICE_COUNT>1, :278-279).
+//
+// HBM-bound: each CTA handles one token row (b,s); every thread owns one 16-byte vector of
+// the first half of a head and its partner vector in the second half, so all global
+// accesses are 16-byte and coalesced over d.  cos/sin are read once per row into
+// registers and reused across all Q and K heads.  Algorithmic bytes per token:
+//   2*(Hq+Hk)*D*bytes (read+write) + D*table_bytes (first halves of cos and sin).
+//
+// `compute_dtype` reproduces the reference's rounding: the no-index
+// kernel evaluates in the TABLE dtype, the QK kernel in the promoted dtype; each product
+// and the sum round to that dtype.
+#include "common.cuh"
+
+namespace ub {
+
+template <typename T>
+__global__ void __launch_bounds__(512) rope_kernel(
+    T* Q, int64_t q_bs, int64_t q_hs, int64_t q_ss, T* K, int64_t k_bs, int64_t k_hs,
+    int64_t k_ss, const void* __restrict__ cos, int64_t cos_rs, const void* __restrict__ sin,
+    int64_t sin_rs, const int32_t* __restrict__ indices, int seqlen, int n_heads_q,
+    int n_heads_k, int head_dim, int backward, int table_dt, int comp_dt, int64_t n_rows) {
+  constexpr int V = DT<T>::VEC;
+  const int half = head_dim >> 1;
+  const int vec_per_half = half / V;                 // threads per head
+  const int heads_per_pass = blockDim.x / vec_per_half;
+  const int lane_v = threadIdx.x % vec_per_half;     // which vector inside the half
+  const int head_in_pass = threadIdx.x / vec_per_half;
+  const int d0 = lane_v * V;
+  const int total_heads = n_heads_q + n_heads_k;
+
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int b = (int)(row / seqlen);
+    const int s = (int)(row - (int64_t)b * seqlen);
+    const int pos = indices ? indices[row] : s;
+    float c[V], sn[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      c[i] = load_as_f(cos, table_dt, (int64_t)pos * cos_rs + d0 + i);
+      float sv = load_as_f(sin, table_dt, (int64_t)pos * sin_rs + d0 + i);
+      sn[i] = backward ? -sv : sv;
+    }
+    if (head_in_pass >= heads_per_pass) continue;
+    for (int h = head_in_pass; h < total_heads; h += heads_per_pass) {
+      T* p = (h < n_heads_q)
+                 ? Q + (int64_t)b * q_bs + (int64_t)h * q_hs + (int64_t)s * q_ss
+                 : K + (int64_t)b * k_bs + (int64_t)(h - n_heads_q) * k_hs + (int64_t)s * k_ss;
+      float x1[V], x2[V], o1[V], o2[V];
+      load_vec<T>(p + d0, x1);
+      load_vec<T>(p + half + d0, x2);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float a1 = round_to(comp_dt, x1[i]), a2 = round_to(comp_dt, x2[i]);
+        // q1*cos - q2*sin ; q2*cos + q1*sin, each op rounded to the compute dtype
+        const float m11 = round_to(comp_dt, __fmul_rn(a1, c[i]));
+        const float m22 = round_to(comp_dt, __fmul_rn(a2, sn[i]));
+        const float m21 = round_to(comp_dt, __fmul_rn(a2, c[i]));
+        const float m12 = round_to(comp_dt, __fmul_rn(a1, sn[i]));
+        o1[i] = round_to(comp_dt, __fsub_rn(m11, m22));
+        o2[i] = round_to(comp_dt, __fadd_rn(m21, m12));
+      }
+      store_vec<T>(p + d0, o1);
+      store_vec<T>(p + half + d0, o2);
+    }
+  }
+}
+
+}  // namespace ub
+
+extern "C" int ub200_rope_qk(void* Q, int64_t q_batch_stride, int64_t q_head_stride,
+                             int64_t q_seq_stride, void* K, int64_t k_batch_stride,
+                             int64_t k_head_stride, int64_t k_seq_stride, const void* cos,
+                             int64_t cos_row_stride, const void* sin, int64_t sin_row_stride,
+                             const int32_t* indices, int batch, int seqlen, int n_heads_q,
+                             int n_heads_k, int head_dim, int backward, int dtype,
+                             int table_dtype, int compute_dtype, cudaStream_t stream) {
+  using namespace ub;
+  const int64_t n_rows = (int64_t)batch * seqlen;
+  if (n_rows <= 0) return UB200_OK;
+  const int V = dtype == UB200_F32 ? 4 : 8;
+  const int half = head_dim / 2;
+  if (head_dim % 2 || half % V) return UB200_ERR_BAD_ARG;
+  if (q_batch_stride % V || q_head_stride % V || q_seq_stride % V) return UB200_ERR_BAD_ARG;
+  if (K == nullptr) n_heads_k = 0;
+  if (n_heads_k && (k_batch_stride % V || k_head_stride % V || k_seq_stride % V))
+    return UB200_ERR_BAD_ARG;
+  const int vec_per_half = half / V;
+  if (vec_per_half > 512) return UB200_ERR_UNSUPPORTED;
+  // one pass over all heads if it fits in 256 threads
+  int heads = n_heads_q + n_heads_k;
+  int threads = vec_per_half * heads;
+  if (threads > 512) threads = (512 / vec_per_half) * vec_per_half;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  int64_t g = (int64_t)UB_SM_COUNT * 8;
+  const int grid = (int)(n_rows < g ? n_rows : g);
+#define GO(T)                                                                                  \
+  rope_kernel<T><<<grid, threads, 0, stream>>>(                                                \
+      (T*)Q, q_batch_stride, q_head_stride, q_seq_stride, (T*)K, k_batch_stride, k_head_stride, \
+      k_seq_stride, cos, cos_row_stride, sin, sin_row_stride, indices, seqlen, n_heads_q,       \
+      n_heads_k, head_dim, backward, table_dtype, compute_dtype, n_rows)
+  if (dtype == UB200_BF16) { GO(__nv_bfloat16); }
+  else if (dtype == UB200_F16) { GO(__half); }
+  else if (dtype == UB200_F32) { GO(float); }
+  else return UB200_ERR_BAD_ARG;
+#undef GO
+  UB_RETURN_LAST();
+}

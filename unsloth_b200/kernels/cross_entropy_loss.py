@@ -1,0 +1,139 @@
+"""Cross entropy -- host-side mirror of unsloth/kernels/cross_entropy_loss.py:288-449 and of
+the external logits-free loss the reference calls at models/llama.py:1497-1509
+(`unsloth_zoo.loss_utils.unsloth_fused_ce_loss`).
+
+  * `Fast_CrossEntropyLoss` / `fast_cross_entropy_loss`: materialised logits, in-place gradient
+    (the gradient overwrites the logits buffer, cross_entropy_loss.py:380-418).
+  * `unsloth_fused_ce_loss`: chunked linear + CE that never materialises the full [T, V] logits:
+    per row-chunk a tcgen05 GEMM produces the logits chunk, the CE kernels turn it into the
+    gradient chunk in place, and a second GEMM (lm_head consumed as an MN-major operand)
+    reduces it to dHidden.  Labels are shifted inside (llama.py:1479-1482).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib as L
+from .utils import MAX_FUSED_SIZE, gemm  # noqa: F401
+
+
+def _ce_forward(logits2, labels1, softcap, scale):
+    n_rows, vocab = logits2.shape
+    losses = torch.empty(n_rows, dtype=torch.float32, device=logits2.device)
+    lse = torch.empty(n_rows, dtype=torch.float32, device=logits2.device)
+    L.call("ub200_cross_entropy_fwd", L.ptr(logits2), logits2.stride(0), L.ptr(labels1), L.ptr(losses),
+           L.ptr(lse), n_rows, vocab, float(softcap), float(scale), L.dt(logits2), L.stream())
+    return losses, lse
+
+
+def _ce_backward_(logits2, lse, labels1, dloss, dloss_stride, softcap, scale):
+    n_rows, vocab = logits2.shape
+    L.call("ub200_cross_entropy_bwd", L.ptr(logits2), logits2.stride(0), L.ptr(lse), L.ptr(labels1),
+           L.ptr(dloss), int(dloss_stride), n_rows, vocab, float(softcap), float(scale),
+           L.dt(logits2), L.stream())
+    return logits2
+
+
+class Fast_CrossEntropyLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, logit_softcapping: float = 0, logit_scaling: float = 0):
+        L.require_cuda(logits)
+        assert logits.dim() == 2 and logits.stride(-1) == 1
+        labels = labels.to(logits.device)
+        if labels.dtype != torch.int64:
+            labels = labels.to(torch.int64)
+        labels = labels.contiguous()
+        losses, lse = _ce_forward(logits, labels, logit_softcapping or 0.0, logit_scaling or 0.0)
+        ctx.save_for_backward(logits, lse, labels)
+        ctx.logit_softcapping = logit_softcapping or 0.0
+        ctx.logit_scaling = logit_scaling or 0.0
+        return losses
+
+    @staticmethod
+    def backward(ctx, dlosses):
+        logits, lse, labels = ctx.saved_tensors
+        dl = dlosses if dlosses.dtype == torch.float32 else dlosses.float()
+        stride = dl.stride(0) if dl.numel() > 1 else 0
+        _ce_backward_(logits, lse, labels, dl, stride, ctx.logit_softcapping, ctx.logit_scaling)
+        return logits, None, None, None
+
+
+def fast_cross_entropy_loss(logits, labels, logit_softcapping=0, logit_scaling=0, n_items=None):
+    """cross_entropy_loss.py:421-449.  logits [B,S,V], labels [B,S] (already shifted)."""
+    batch, seq_len, d = logits.shape
+    assert labels.shape == (batch, seq_len)
+    device = logits.device
+    loss = Fast_CrossEntropyLoss.apply(logits.view(batch * seq_len, d), labels.view(-1),
+                                       logit_softcapping, logit_scaling)
+    if n_items is None:
+        n_items = torch.count_nonzero(labels != -100)
+    if torch.is_tensor(n_items):
+        n_items = n_items.to(device)
+    return loss.sum() / n_items
+
+
+class Fused_Linear_CrossEntropy(torch.autograd.Function):
+    """hidden [T,H] x lm_head [V,H] -> scalar sum of per-row losses / n_items, dHidden computed
+    in the same pass (gradient of the mean loss), scaled by the incoming grad in backward."""
+
+    @staticmethod
+    def forward(ctx, hidden2, weight, labels1, inv_n, softcap, scale, chunk_rows):
+        L.require_cuda(hidden2, weight)
+        T, H = hidden2.shape
+        V = weight.shape[0]
+        dev, dt = hidden2.device, hidden2.dtype
+        W = weight if weight.dtype == dt else weight.to(dt)
+        W = W if W.stride(-1) == 1 else W.contiguous()
+        losses = torch.empty(T, dtype=torch.float32, device=dev)
+        dH = torch.empty((T, H), dtype=dt, device=dev)
+        chunk_rows = max(128, min(chunk_rows, T))
+        buf = torch.empty((chunk_rows, V), dtype=dt, device=dev)
+        for r0 in range(0, T, chunk_rows):
+            r1 = min(T, r0 + chunk_rows)
+            n = r1 - r0
+            logits = buf[:n]
+            gemm(n, V, [(hidden2[r0:r1], W, H)], logits)
+            lab = labels1[r0:r1]
+            l, lse = _ce_forward(logits, lab, softcap, scale)
+            losses[r0:r1] = l
+            _ce_backward_(logits, lse, lab, inv_n, 0, softcap, scale)      # logits <- d logits
+            gemm(n, H, [(logits, W, V)], dH[r0:r1], a_mn=False, b_mn=True)  # d hidden
+        ctx.save_for_backward(dH)
+        return losses.sum() * inv_n.squeeze()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dH,) = ctx.saved_tensors
+        return dH * dloss.to(dH.dtype), None, None, None, None, None, None
+
+
+def unsloth_fused_ce_loss(trainer=None, hidden_states=None, lm_head_weight=None, lm_head_bias=None,
+                          labels=None, mask=None, n_items=None, scaling=None, target_gb=None,
+                          torch_compile=False, logit_softcapping=0, chunk_rows=2048, **kwargs):
+    """Drop-in for `unsloth_zoo.loss_utils.unsloth_fused_ce_loss` at the reference call sites
+    models/llama.py:1497-1509 and models/mistral.py:352-364.  hidden_states [B,S,H], labels [B,S]
+    UNSHIFTED; divides by n_items (count of non-ignored shifted labels when None).  Returns a
+    fresh 0-d tensor (HF Trainer multiplies the loss in place, models/_utils.py:3200-3225)."""
+    if lm_head_bias is not None:
+        raise NotImplementedError("unsloth_b200: lm_head bias is not supported on the fused CE path")
+    if getattr(lm_head_weight, "requires_grad", False):
+        raise NotImplementedError("unsloth_b200: trainable lm_head is not supported on the fused CE path")
+    B, S, H = hidden_states.shape
+    dev = hidden_states.device
+    shift = torch.full_like(labels, -100)
+    shift[..., :-1] = labels[..., 1:]
+    if mask is not None:
+        shift = torch.where(mask.to(torch.bool), shift, torch.full_like(shift, -100))
+    shift = shift.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+    if n_items is None:
+        n_items = torch.count_nonzero(shift != -100)
+    if torch.is_tensor(n_items):
+        inv_n = (1.0 / n_items.to(device=dev, dtype=torch.float32)).reshape(1)
+    else:
+        inv_n = torch.full((1,), 1.0 / float(n_items), dtype=torch.float32, device=dev)
+    h2 = hidden_states.reshape(-1, H)
+    if h2.stride(-1) != 1:
+        h2 = h2.contiguous()
+    return Fused_Linear_CrossEntropy.apply(h2, lm_head_weight, shift, inv_n,
+                                           float(logit_softcapping or 0), float(scaling or 0),
+                                           int(chunk_rows))

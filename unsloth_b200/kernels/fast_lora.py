@@ -1,0 +1,333 @@
+"""LoRA_MLP / LoRA_QKV / LoRA_W -- host-side mirror of unsloth/kernels/fast_lora.py.
+
+Same classes, `apply_*` entry points, argument order and gradient slots as the reference
+(fast_lora.py:28-229, 235-332, 335-571, 574-657).  The hand-derived backward is the same
+algebra (fast_lora.py:42-62); what changes is how it is executed on a B200:
+
+  * every projection is ONE multi-segment tcgen05 GEMM (csrc/gemm_tcgen05.cu): base weight and
+    the rank-r update `(X A^T)(s B^T)` accumulate in the same fp32 TMEM accumulator -- the
+    reference issues a cuBLAS GEMM plus an `addmm_` and rounds to bf16 in between;
+  * projections that share an input (q/k/v, gate/up) share ONE skinny GEMM `X @ [A_q;A_k;A_v]^T`
+    into a zero-padded 64-wide rank block;
+  * dX of a group is ONE launch: sum_i dY_i @ W_i + G @ A_cat, with W_i consumed as an MN-major
+    operand straight from the [out,in] dequantised buffer (no transpose, no running bf16 sum);
+  * dA / dB are split-K reductions over tokens with both operands MN-major (X^T @ G, dY^T @ XA),
+    fixed reduction order (deterministic), fp32 results (the reference returns bf16-precision
+    grads, fast_lora.py:172-189).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib as L
+from .utils import (RANK_BLOCK, as_b_operand, cast_pad, dense_weight, gemm,
+                    get_lora_parameters, get_lora_parameters_bias, matmul_lora)  # noqa: F401
+from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
+from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
+                    geglu_approx_forward_kernel, geglu_approx_backward_kernel)
+
+_SM = 148
+
+
+def _as2d(t):
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(-1) != 1 or (t2.stride(0) % 8) or (t2.data_ptr() % 16):
+        t2 = t2.contiguous()
+    return t2
+
+
+def _split_k(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 63) // 64 if N <= 64 else (N + 127) // 128)
+    kb = (K + 63) // 64
+    return max(1, min(_SM // max(tiles, 1), kb // 4 if kb >= 4 else 1))
+
+
+class _Group:
+    """Projections (W, W_quant, A, B, s) that share one 2-D input X2 [T, in]."""
+
+    def __init__(self, X2, projs):
+        self.X2 = X2
+        self.projs = projs
+        self.T, self.in_f = X2.shape
+        self.dtype = X2.dtype
+        self.dev = X2.device
+        self.offs, off = [], 0
+        for (_, _, A, _, _) in projs:
+            self.offs.append(off)
+            off += 0 if A is None else A.shape[0]
+        self.rank_total = off
+        self.has_lora = off > 0
+        self.Rp = ((off + RANK_BLOCK - 1) // RANK_BLOCK) * RANK_BLOCK
+        self._A_cat = None
+
+    # [Rp, in] : rows offs[i].. hold A_i in the compute dtype, zero elsewhere
+    def A_cat(self):
+        if self._A_cat is None:
+            A_cat = torch.empty((self.Rp, self.in_f), dtype=self.dtype, device=self.dev)
+            blocks = [(o, A) for o, (_, _, A, _, _) in zip(self.offs, self.projs) if A is not None]
+            for j, (o, A) in enumerate(blocks):
+                end = blocks[j + 1][0] if j + 1 < len(blocks) else self.Rp
+                A = A if A.stride(-1) == 1 else A.contiguous()
+                cast_pad(A, A_cat[o:end])
+            self._A_cat = A_cat
+        return self._A_cat
+
+    def forward(self):
+        """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None."""
+        X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
+        XA = None
+        if self.has_lora:
+            XA = gemm(T, self.Rp, [(X2, self.A_cat(), self.in_f)],
+                      torch.empty((T, self.Rp), dtype=dt, device=dev))
+        outs = []
+        for off, (W, Wq, A, B, s) in zip(self.offs, self.projs):
+            Wd = dense_weight(W, Wq, dt, 0)
+            Bop, b_mn = as_b_operand(Wd)
+            N = Wd.shape[0]
+            segs = [(X2, Bop, self.in_f)]
+            if A is not None:
+                Bc = B if B.stride(-1) == 1 else B.contiguous()
+                if b_mn:
+                    B_pad = cast_pad(Bc, torch.empty((self.Rp, N), dtype=dt, device=dev),
+                                     row_off=off, scale=s, transpose=True)
+                else:
+                    B_pad = cast_pad(Bc, torch.empty((N, self.Rp), dtype=dt, device=dev),
+                                     col_off=off, scale=s)
+                segs.append((XA, B_pad, self.Rp))
+            Y = torch.empty((T, N), dtype=dt, device=dev)
+            gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
+            outs.append(Y)
+        return outs, XA
+
+    def backward(self, dYs, XA, dX_out=None):
+        """dYs: list of [T, out_i].  Returns (dX [T,in], [(dA_i, dB_i) or (None, None)])."""
+        X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
+        grads = []
+        G = None
+        if self.has_lora:
+            # G[T, Rp] = sum_i dY_i @ (s_i B_i) placed at the adapter's rank slot
+            segs = []
+            for off, dY, (W, Wq, A, B, s) in zip(self.offs, dYs, self.projs):
+                if A is None:
+                    continue
+                Bc = B if B.stride(-1) == 1 else B.contiguous()
+                out_f = Bc.shape[0]
+                BT_pad = cast_pad(Bc, torch.empty((Rp, out_f), dtype=dt, device=dev),
+                                  row_off=off, scale=s, transpose=True)
+                segs.append((dY, BT_pad, out_f))
+            G = gemm(T, Rp, segs, torch.empty((T, Rp), dtype=dt, device=dev))
+            # dA_cat^T [in, Rp] = X^T @ G   (both operands MN-major, reduction over tokens)
+            dA_catT = torch.empty((self.in_f, Rp), dtype=torch.float32, device=dev)
+            gemm(self.in_f, Rp, [(X2, G, T)], dA_catT, a_mn=True, b_mn=True,
+                 split_k=_split_k(self.in_f, Rp, T))
+            for off, dY, (W, Wq, A, B, s) in zip(self.offs, dYs, self.projs):
+                if A is None:
+                    grads.append((None, None))
+                    continue
+                r = A.shape[0]
+                out_f = dY.shape[1]
+                # dB_i [out, Rp] = s_i * dY_i^T @ XA ; keep this adapter's columns
+                dB_full = torch.empty((out_f, Rp), dtype=torch.float32, device=dev)
+                gemm(out_f, Rp, [(dY, XA, T)], dB_full, a_mn=True, b_mn=True, alpha=s,
+                     split_k=_split_k(out_f, Rp, T))
+                grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
+        else:
+            grads = [(None, None)] * len(self.projs)
+        # dX = sum_i dY_i @ W_i  +  G @ A_cat      (one launch; W_i as MN-major operands)
+        segs = []
+        for slot, (dY, (W, Wq, A, B, s)) in enumerate(zip(dYs, self.projs)):
+            Wd = dense_weight(W, Wq, dt, slot)          # logical [out, in]
+            # as the B operand of dY @ Wd we need [N=in, K=out]: that is Wd^T
+            Bop, b_mn = as_b_operand(Wd.t())
+            if not b_mn:
+                # Wd^T has contiguous rows only if Wd was itself a transposed view: fall back to
+                # a materialised [in, out] copy so all segments share the MN-major layout
+                Bop, b_mn = Bop.t().contiguous(), True
+            segs.append((dY, Bop, dY.shape[1]))
+        if self.has_lora:
+            segs.append((G, self.A_cat(), Rp))
+        dX = dX_out if dX_out is not None else torch.empty((T, self.in_f), dtype=dt, device=dev)
+        gemm(T, self.in_f, segs, dX, a_mn=False, b_mn=True)
+        return dX, grads
+
+
+class LoRA_MLP(torch.autograd.Function):
+    """fast_lora.py:28-229.  i = down(act(gate(X)) * up(X)), each projection NF4 + LoRA."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, X, gateW, gateW_quant, gateA, gateB, gateS, upW, upW_quant, upA, upB, upS,
+                downW, downW_quant, downA, downB, downS, _forward_function, _backward_function,
+                inplace=True):
+        L.require_cuda(X)
+        shape = X.shape
+        X2 = _as2d(X)
+        grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
+        (e, g), XA1 = grp.forward()
+        b_s = shape[:-1]
+        h = _forward_function(e.view(*b_s, -1) if X.dim() == 3 else e.view(1, *e.shape),
+                              g.view(*b_s, -1) if X.dim() == 3 else g.view(1, *g.shape))
+        h2 = h.reshape(-1, h.shape[-1])
+        grp2 = _Group(h2, [(downW, downW_quant, downA, downB, downS)])
+        (i,), XA2 = grp2.forward()
+        ctx.custom_saved_tensors = (gateW, gateW_quant, gateS, upW, upW_quant, upS, downW,
+                                    downW_quant, downS, _backward_function)
+        ctx.save_for_backward(gateA, gateB, upA, upB, downA, downB, X2, e, g, XA1, XA2)
+        ctx.inplace = inplace
+        ctx.shape = shape
+        return i.view(*b_s, -1)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dY):
+        (gateW, gateW_quant, gateS, upW, upW_quant, upS, downW, downW_quant, downS,
+         _backward_function) = ctx.custom_saved_tensors
+        gateA, gateB, upA, upB, downA, downB, X2, e, g, XA1, XA2 = ctx.saved_tensors
+        dY2 = _as2d(dY)
+        T = X2.shape[0]
+        dt, dev = X2.dtype, X2.device
+        # --- down projection: DW = dY @ W_down + (dY @ s B_down) @ A_down          (:155)
+        # `h` is not needed yet: a group over a placeholder input gives DW and G_down
+        down = _Group(e, [(downW, downW_quant, downA, downB, downS)])  # in_f = I (e is [T, I])
+        G_down = None
+        segs = []
+        Wd = dense_weight(downW, downW_quant, dt, 0)                   # [H, I]
+        Bop, b_mn = as_b_operand(Wd.t())
+        if not b_mn:
+            Bop, b_mn = Bop.t().contiguous(), True
+        segs.append((dY2, Bop, dY2.shape[1]))
+        if downA is not None:
+            Bc = downB if downB.stride(-1) == 1 else downB.contiguous()
+            BT_pad = cast_pad(Bc, torch.empty((down.Rp, Bc.shape[0]), dtype=dt, device=dev),
+                              scale=downS, transpose=True)
+            G_down = gemm(T, down.Rp, [(dY2, BT_pad, Bc.shape[0])],
+                          torch.empty((T, down.Rp), dtype=dt, device=dev))
+            segs.append((G_down, down.A_cat(), down.Rp))
+        DW = torch.empty((T, e.shape[1]), dtype=dt, device=dev)
+        gemm(T, e.shape[1], segs, DW, a_mn=False, b_mn=True)
+        # --- activation backward, in place: DW <- h, e <- df, g <- de            (:156-157)
+        h, df, de = _backward_function(DW, e, g)
+        # --- down LoRA grads                                                      (:171-172)
+        d_downA = d_downB = None
+        if downA is not None:
+            r = downA.shape[0]
+            I = h.shape[1]
+            dA_T = torch.empty((I, down.Rp), dtype=torch.float32, device=dev)
+            gemm(I, down.Rp, [(h, G_down, T)], dA_T, a_mn=True, b_mn=True,
+                 split_k=_split_k(I, down.Rp, T))
+            Hout = dY2.shape[1]
+            dB_full = torch.empty((Hout, down.Rp), dtype=torch.float32, device=dev)
+            gemm(Hout, down.Rp, [(dY2, XA2, T)], dB_full, a_mn=True, b_mn=True, alpha=downS,
+                 split_k=_split_k(Hout, down.Rp, T))
+            d_downA, d_downB = dA_T[:, :r].t(), dB_full[:, :r]
+        # --- gate / up: LoRA grads and dX (into the saved X buffer when inplace)   (:178-204)
+        grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
+        dX, ((d_gateA, d_gateB), (d_upA, d_upB)) = grp.backward(
+            [de, df], XA1, dX_out=X2 if ctx.inplace else None)
+        return (dX.view(ctx.shape), None, None, d_gateA, d_gateB, None, None, None, d_upA, d_upB,
+                None, None, None, d_downA, d_downB, None, None, None, None)
+
+
+def apply_lora_mlp_swiglu(self, X, inplace=True):
+    """fast_lora.py:235-265."""
+    gateW, gateW_quant, gateA, gateB, gateS = get_lora_parameters(self.gate_proj)
+    upW, upW_quant, upA, upB, upS = get_lora_parameters(self.up_proj)
+    downW, downW_quant, downA, downB, downS = get_lora_parameters(self.down_proj)
+    return LoRA_MLP.apply(X, gateW, gateW_quant, gateA, gateB, gateS, upW, upW_quant, upA, upB,
+                          upS, downW, downW_quant, downA, downB, downS, swiglu_fg_kernel,
+                          swiglu_DWf_DW_dfg_kernel, inplace)
+
+
+def apply_lora_mlp_geglu_exact(self, X, inplace=True):
+    """fast_lora.py:271-301."""
+    gateW, gateW_quant, gateA, gateB, gateS = get_lora_parameters(self.gate_proj)
+    upW, upW_quant, upA, upB, upS = get_lora_parameters(self.up_proj)
+    downW, downW_quant, downA, downB, downS = get_lora_parameters(self.down_proj)
+    return LoRA_MLP.apply(X, gateW, gateW_quant, gateA, gateB, gateS, upW, upW_quant, upA, upB,
+                          upS, downW, downW_quant, downA, downB, downS,
+                          geglu_exact_forward_kernel, geglu_exact_backward_kernel, inplace)
+
+
+def apply_lora_mlp_geglu_approx(self, X):
+    """fast_lora.py:307-332 (no `inplace` argument, as in the reference)."""
+    gateW, gateW_quant, gateA, gateB, gateS = get_lora_parameters(self.gate_proj)
+    upW, upW_quant, upA, upB, upS = get_lora_parameters(self.up_proj)
+    downW, downW_quant, downA, downB, downS = get_lora_parameters(self.down_proj)
+    return LoRA_MLP.apply(X, gateW, gateW_quant, gateA, gateB, gateS, upW, upW_quant, upA, upB,
+                          upS, downW, downW_quant, downA, downB, downS,
+                          geglu_approx_forward_kernel, geglu_approx_backward_kernel)
+
+
+class LoRA_QKV(torch.autograd.Function):
+    """fast_lora.py:335-540."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, X, QW, QW_quant, QA, QB, QS, KW, KW_quant, KA, KB, KS, VW, VW_quant, VA, VB,
+                VS, inplace=True):
+        L.require_cuda(X)
+        shape = X.shape
+        X2 = _as2d(X)
+        grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
+                          (VW, VW_quant, VA, VB, VS)])
+        (Q, K, V), XA = grp.forward()
+        if len(shape) == 3:
+            Q, K, V = (t.view(shape[0], shape[1], -1) for t in (Q, K, V))
+        ctx.custom_saved_tensors = (QW, QW_quant, QS, KW, KW_quant, KS, VW, VW_quant, VS)
+        ctx.save_for_backward(X2, QA, QB, KA, KB, VA, VB, XA)
+        ctx.inplace = inplace
+        ctx.shape = shape
+        return Q, K, V
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dQ, dK, dV):
+        QW, QW_quant, QS, KW, KW_quant, KS, VW, VW_quant, VS = ctx.custom_saved_tensors
+        X2, QA, QB, KA, KB, VA, VB, XA = ctx.saved_tensors
+        grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
+                          (VW, VW_quant, VA, VB, VS)])
+        dX, ((dQA, dQB), (dKA, dKB), (dVA, dVB)) = grp.backward(
+            [_as2d(dQ), _as2d(dK), _as2d(dV)], XA, dX_out=X2 if ctx.inplace else None)
+        return (dX.view(ctx.shape), None, None, dQA, dQB, None, None, None, dKA, dKB, None, None,
+                None, dVA, dVB, None, None)
+
+
+def apply_lora_qkv(self, X, inplace=True):
+    """fast_lora.py:543-571."""
+    QW, QW_quant, QA, QB, QS = get_lora_parameters(self.q_proj)
+    KW, KW_quant, KA, KB, KS = get_lora_parameters(self.k_proj)
+    VW, VW_quant, VA, VB, VS = get_lora_parameters(self.v_proj)
+    return LoRA_QKV.apply(X, QW, QW_quant, QA, QB, QS, KW, KW_quant, KA, KB, KS, VW, VW_quant,
+                          VA, VB, VS, inplace)
+
+
+class LoRA_W(torch.autograd.Function):
+    """fast_lora.py:574-650 (o_proj)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, X, W, W_quant, A, B, S):
+        L.require_cuda(X)
+        shape = X.shape
+        X2 = _as2d(X)
+        grp = _Group(X2, [(W, W_quant, A, B, S)])
+        (XW,), XA = grp.forward()
+        ctx.custom_saved_tensors = (W, W_quant, S)
+        ctx.save_for_backward(A, B, X2, XA)
+        ctx.shape = shape
+        return XW.view(*shape[:-1], -1)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dY):
+        W, W_quant, S = ctx.custom_saved_tensors
+        A, B, X2, XA = ctx.saved_tensors
+        grp = _Group(X2, [(W, W_quant, A, B, S)])
+        dX, ((dA, dB),) = grp.backward([_as2d(dY)], XA)
+        return dX.view(ctx.shape), None, None, dA, dB, None
+
+
+def apply_lora_o(self, X):
+    """fast_lora.py:653-657."""
+    OW, OW_quant, OA, OB, OS = get_lora_parameters(self.o_proj)
+    return LoRA_W.apply(X, OW, OW_quant, OA, OB, OS)

@@ -1,0 +1,208 @@
+"""Host-side mirror of unsloth/kernels/utils.py for the hot path:
+`fast_dequantize` (:567-679), `matmul_lora` (:1128-1170), `get_lora_parameters[_bias]`
+(:335-440), `QUANT_STATE`, plus the thin `gemm` wrapper over ub200_gemm.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _lib as L
+
+MAX_FUSED_SIZE = 65536
+RANK_BLOCK = 64  # the GEMM's K block: LoRA rank blocks are zero-padded to a multiple of it
+
+
+def QUANT_STATE(W):
+    return getattr(W, "quant_state", None)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-device reusable dequantised-weight buffers (the reference's WEIGHT_BUFFERS,
+# kernels/utils.py:613-637, generalised to several slots because one multi-segment GEMM
+# can consume several dequantised weights at once).  Stream ordering makes reuse safe.
+# ---------------------------------------------------------------------------------------------
+_WEIGHT_BUFFERS = {}
+
+
+def _weight_buffer(device, slot, numel, dtype):
+    key = (device.index, slot, dtype)
+    buf = _WEIGHT_BUFFERS.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(numel, dtype=dtype, device=device, requires_grad=False)
+        _WEIGHT_BUFFERS[key] = buf
+    return buf[:numel]
+
+
+def _unpack_quant_state(quant_state):
+    if type(quant_state) is not list:
+        s2 = quant_state.state2
+        return (quant_state.absmax, quant_state.shape, quant_state.dtype, quant_state.blocksize,
+                quant_state.offset, s2.absmax, s2.code, s2.blocksize)
+    # old list form (kernels/utils.py:594-598)
+    absmax, shape, dtype, blocksize, compressed_stats, _, _ = quant_state
+    offset, state2 = compressed_stats
+    absmax2, code2, blocksize2, _, _, _, _ = state2
+    return absmax, shape, dtype, blocksize, offset, absmax2, code2, blocksize2
+
+
+@torch.inference_mode
+def fast_dequantize(W, quant_state=None, out=None, use_global_buffer=False, _slot=0):
+    """NF4 double-quant -> quant_state.dtype.  Same contract as the reference
+    (kernels/utils.py:567-679): `quant_state is None` returns W unchanged; `out=` must match
+    shape/dtype; returns `out.t()` iff `W.shape[0] == 1` (packed weight passed transposed)."""
+    if quant_state is None:
+        return W
+    L.require_cuda(W)
+    absmax, shape, dtype, blocksize, offset, absmax2, code2, blocksize2 = _unpack_quant_state(quant_state)
+    device = W.device
+    numel = shape[0] * shape[1]
+    if use_global_buffer:
+        out = _weight_buffer(device, _slot, numel, dtype).view(shape)
+    elif out is None:
+        out = torch.empty(shape, dtype=dtype, device=device, requires_grad=False)
+    else:
+        assert out.shape == shape
+        assert out.dtype == dtype
+    if not torch.is_tensor(offset):
+        offset = torch.tensor(float(offset), dtype=torch.float32, device=device)
+    L.call("ub200_dequantize_nf4", L.ptr(W), L.ptr(absmax), L.ptr(code2), L.ptr(absmax2),
+           L.ptr(offset), L.ptr(out), numel, int(blocksize), int(blocksize2), L.dt(dtype), L.stream())
+    is_transposed = True if W.shape[0] == 1 else False
+    return out.t() if is_transposed else out
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------
+def _check_operand(t):
+    if t.stride(-1) != 1 or t.dim() != 2:
+        raise RuntimeError("unsloth_b200.gemm: operands must be 2-D with a contiguous last dim")
+
+
+def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, split_k=1,
+         block_n=0):
+    """out[M,N] (+)= alpha * sum_s A_s . B_s^T on the tcgen05 tensor cores.
+
+    segs: list of (A, B, K).  a_mn=False: A is [M, K]; True: A is [K, M] (row-major).
+    b_mn=False: B is [N, K]; True: B is [K, N]."""
+    n = len(segs)
+    arr = (L.GemmSegment * n)()
+    ab_dtype = segs[0][0].dtype
+    for i, (A, B, K) in enumerate(segs):
+        _check_operand(A); _check_operand(B)
+        if A.dtype != ab_dtype or B.dtype != ab_dtype:
+            raise RuntimeError("unsloth_b200.gemm: mixed operand dtypes %s/%s" % (A.dtype, B.dtype))
+        arr[i].a = A.data_ptr(); arr[i].lda = A.stride(0)
+        arr[i].b = B.data_ptr(); arr[i].ldb = B.stride(0)
+        arr[i].k = K
+    ws = None
+    if split_k > 1:
+        ws = torch.empty(split_k * M * N, dtype=torch.float32, device=out.device)
+    L.call("ub200_gemm", M, N, arr, n, int(a_mn), int(b_mn), L.dt(ab_dtype), L.ptr(out),
+           out.stride(0), L.dt(out), float(alpha), int(accumulate), int(split_k), L.ptr(ws),
+           int(block_n), L.stream())
+    return out
+
+
+def cast_pad(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
+    """dst (2-D, fully overwritten) <- zeros with scale*src (optionally transposed) placed at
+    (row_off, col_off)."""
+    L.call("ub200_cast_pad_2d", L.ptr(src), L.dt(src), src.stride(0), src.shape[0], src.shape[1],
+           L.ptr(dst), L.dt(dst), dst.stride(0), dst.shape[0], dst.shape[1], int(row_off),
+           int(col_off), float(scale), int(transpose), L.stream())
+    return dst
+
+
+def dense_weight(W, W_quant, dtype, slot=0):
+    """Logical [N_out, K_in] weight in the compute dtype, exactly what the reference's
+    `fast_dequantize(W, W_quant)` hands to `torch.matmul(X, W.t())`: a reusable-slot dequantised
+    buffer (a transposed VIEW of it when the packed weight was passed as `W.t()`), or W itself
+    for 16-bit LoRA."""
+    Wd = fast_dequantize(W, W_quant, use_global_buffer=True, _slot=slot) if W_quant is not None else W
+    if Wd.dtype != dtype:
+        Wd = Wd.to(dtype)
+    return Wd
+
+
+def as_b_operand(Wd):
+    """(tensor, b_mn) for a logical [N, K] matrix: K-major if rows are contiguous, MN-major
+    (the [K, N] row-major buffer underneath) if it is a transposed view."""
+    if Wd.stride(-1) == 1:
+        return Wd, False
+    if Wd.stride(0) == 1:
+        return Wd.t(), True
+    return Wd.contiguous(), False
+
+
+def matmul_lora(X, W, W_quant, A, B, s, out=None):
+    """out = X @ dequant(W).T + (X @ A.T) @ (s * B.T)   (kernels/utils.py:1128-1170).
+    A: [r, K_in], B: [N_out, r] (possibly transposed views, as the reference's backward passes
+    them).  One tcgen05 launch for the sum: the LoRA update rides as an extra K block of the
+    same fp32 accumulator (single rounding; the reference rounds the base product to bf16
+    first, then `addmm_`)."""
+    L.require_cuda(X)
+    dtype = X.dtype
+    reshape = X.dim() == 3
+    if reshape:
+        batch, seq_len, _ = X.shape
+    X2 = X.reshape(-1, X.shape[-1])
+    if X2.stride(-1) != 1:
+        X2 = X2.contiguous()
+    T, K = X2.shape
+    Wd = dense_weight(W, W_quant, dtype, 0)
+    N = Wd.shape[0]
+    assert Wd.shape[1] == K, (tuple(Wd.shape), tuple(X2.shape))
+    Bop, b_mn = as_b_operand(Wd)
+    out2 = torch.empty((T, N), dtype=dtype, device=X.device) if out is None else out.reshape(T, N)
+    segs = [(X2, Bop, K)]
+    if A is not None:
+        A = A if A.stride(-1) == 1 else A.contiguous()
+        B = B if B.stride(-1) == 1 else B.contiguous()
+        r = A.shape[0]
+        Rp = ((r + RANK_BLOCK - 1) // RANK_BLOCK) * RANK_BLOCK
+        A_pad = cast_pad(A, torch.empty((Rp, K), dtype=dtype, device=X.device))
+        XA = gemm(T, Rp, [(X2, A_pad, K)], torch.empty((T, Rp), dtype=dtype, device=X.device))
+        if b_mn:
+            B_pad = cast_pad(B, torch.empty((Rp, N), dtype=dtype, device=X.device), scale=s,
+                             transpose=True)
+        else:
+            B_pad = cast_pad(B, torch.empty((N, Rp), dtype=dtype, device=X.device), scale=s)
+        segs.append((XA, B_pad, Rp))
+    gemm(T, N, segs, out2, a_mn=False, b_mn=b_mn)
+    return out2.view(batch, seq_len, -1) if reshape else out2
+
+
+# ---------------------------------------------------------------------------------------------
+# PEFT attribute scraper (host only) -- kernels/utils.py:335-440
+# ---------------------------------------------------------------------------------------------
+def get_lora_parameters(proj):
+    """Return (W, W_quant, A, B, scaling); A = B = scaling = None when adapters are disabled
+    or merged (kernels/utils.py:335-397)."""
+    base_layer = getattr(proj, "base_layer", proj)
+    W = base_layer.weight
+    W_quant = getattr(W, "quant_state", None)
+    if getattr(proj, "disable_adapters", True) or proj.merged:
+        return W, W_quant, None, None, None
+    adapter = getattr(proj, "active_adapters", None)
+    if adapter is None:
+        adapter = getattr(proj, "active_adapter", ("default"))
+    adapter = adapter[0]
+    return (W, W_quant, proj.lora_A[adapter].weight, proj.lora_B[adapter].weight,
+            proj.scaling[adapter])
+
+
+def get_lora_parameters_bias(proj):
+    """kernels/utils.py:400-440."""
+    base_layer = getattr(proj, "base_layer", proj)
+    W = base_layer.weight
+    W_quant = getattr(W, "quant_state", None)
+    if getattr(proj, "disable_adapters", True) or proj.merged:
+        return W, W_quant, None, None, None, base_layer.bias
+    adapter = getattr(proj, "active_adapters", None)
+    if adapter is None:
+        adapter = getattr(proj, "active_adapter", ("default"))
+    adapter = adapter[0]
+    return (W, W_quant, proj.lora_A[adapter].weight, proj.lora_B[adapter].weight,
+            proj.scaling[adapter], base_layer.bias)
