@@ -56,20 +56,42 @@ def fast_rms_layernorm(layernorm, X: torch.Tensor, gemma: bool = False):
     return Fast_RMS_Layernorm.apply(X, W, eps, gemma)
 
 
-from transformers.models.llama.modeling_llama import LlamaRMSNorm  # noqa: E402
+def _llama_rmsnorm_cls():
+    from transformers.models.llama.modeling_llama import LlamaRMSNorm
+    return LlamaRMSNorm
 
 
-class Unsloth_LlamaRMSNorm(LlamaRMSNorm):
-    def forward(self, X):
-        return fast_rms_layernorm(self, X, gemma=False)
+_UNSLOTH_CLS = None
+
+
+def _unsloth_rmsnorm_cls():
+    """`Unsloth_LlamaRMSNorm` (rms_layernorm.py:261-264), built lazily so that importing the
+    kernels does not import transformers."""
+    global _UNSLOTH_CLS
+    if _UNSLOTH_CLS is None:
+        base = _llama_rmsnorm_cls()
+
+        class Unsloth_LlamaRMSNorm(base):
+            def forward(self, X):
+                return fast_rms_layernorm(self, X, gemma=False)
+
+        Unsloth_LlamaRMSNorm._hf_base = base
+        _UNSLOTH_CLS = Unsloth_LlamaRMSNorm
+    return _UNSLOTH_CLS
+
+
+def __getattr__(name):
+    if name == "Unsloth_LlamaRMSNorm":
+        return _unsloth_rmsnorm_cls()
+    raise AttributeError(name)
 
 
 def patch_rms_layernorm():
     """Class-level route (rms_layernorm.py:261-274): serve a stock HF model."""
     import transformers.models.llama.modeling_llama as m
-    m.LlamaRMSNorm = Unsloth_LlamaRMSNorm
+    m.LlamaRMSNorm = _unsloth_rmsnorm_cls()
 
 
 def unpatch_rms_layernorm():
     import transformers.models.llama.modeling_llama as m
-    m.LlamaRMSNorm = LlamaRMSNorm
+    m.LlamaRMSNorm = _unsloth_rmsnorm_cls()._hf_base
