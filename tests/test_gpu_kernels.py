@@ -247,10 +247,20 @@ def test_nf4_dequant_bit_exact_and_bnb_symbols():
     assert torch.equal(packed.cpu(), packed_r)                       # integer/byte work: bit exact
     assert torch.equal(qs.absmax.cpu(), qs_r.absmax)
     close(qs.state2.absmax, qs_r.state2.absmax, rtol=0, atol=0)
+    # dequantise the ORACLE's state on the GPU: byte-for-byte the oracle's answer.  (The GPU
+    # quantiser's own `offset` = absmax.mean() differs from the CPU mean in the last bit, so
+    # the two quantisers' states are compared field by field above and below instead.)
+    assert abs(qs.offset.item() - qs_r.offset.item()) <= 1e-7 * abs(qs_r.offset.item()) + 1e-9
     Dr = R.dequantize_nf4(packed_r, qs_r)
+    s2r = QuantState(qs_r.state2.absmax.to(DEV), code=qs_r.state2.code.to(DEV), blocksize=256)
+    qs_o = QuantState(qs_r.absmax.to(DEV), qs_r.shape, None, 64, "nf4", torch.bfloat16,
+                      qs_r.offset.to(DEV), s2r)
+    Do = fast_dequantize(packed_r.to(DEV), qs_o)
+    assert torch.equal(Do.cpu().view(torch.int16), Dr.view(torch.int16))   # bit exact
     D = fast_dequantize(packed, qs)
     assert D.dtype == torch.bfloat16 and D.shape == W.shape
-    assert torch.equal(D.cpu().view(torch.int16), Dr.view(torch.int16))   # bit exact
+    assert (D.cpu().view(torch.int16) != Dr.view(torch.int16)).float().mean() < 0.02
+    assert (D.float().cpu() - Dr.float()).abs().max() <= 2.0 ** -8 * Dr.float().abs().max()
     # transposed-call contract and passthrough (kernels/utils.py:578-579, 678-679)
     assert fast_dequantize(packed.t(), qs).shape == (4096, 1024)
     assert fast_dequantize(W, None) is W
@@ -267,7 +277,7 @@ def test_nf4_dequant_bit_exact_and_bnb_symbols():
     L.lib.cdequantize_blockwise_fp32(L.ptr(s2.code), L.ptr(qs.absmax), L.ptr(s2.absmax), L.ptr(out_abs),
                                      s2.blocksize, n_abs, st)
     out_abs += qs.offset
-    close(out_abs, R.dequantize_absmax(qs_r), rtol=0, atol=0)
+    close(out_abs, R.dequantize_absmax(qs_r), rtol=1e-6, atol=0)
     out2 = torch.empty(1024, 4096, dtype=torch.bfloat16, device=DEV)
     L.lib.cdequantize_blockwise_bf16_nf4(None, L.ptr(packed), L.ptr(out_abs), L.ptr(out2), 64, out2.numel(), st)
     assert torch.equal(out2, D)

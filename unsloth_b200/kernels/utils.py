@@ -81,6 +81,10 @@ def _check_operand(t):
         raise RuntimeError("unsloth_b200.gemm: operands must be 2-D with a contiguous last dim")
 
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream
+GEMM_EVENTS = None
+
+
 def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, split_k=1,
          block_n=0):
     """out[M,N] (+)= alpha * sum_s A_s . B_s^T on the tcgen05 tensor cores.
@@ -100,9 +104,16 @@ def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, s
     ws = None
     if split_k > 1:
         ws = torch.empty(split_k * M * N, dtype=torch.float32, device=out.device)
+    ev = GEMM_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.call("ub200_gemm", M, N, arr, n, int(a_mn), int(b_mn), L.dt(ab_dtype), L.ptr(out),
            out.stride(0), L.dt(out), float(alpha), int(accumulate), int(split_k), L.ptr(ws),
            int(block_n), L.stream())
+    if ev is not None:
+        e1.record()
+        ev.append((2.0 * M * N * sum(k for _, _, k in segs), e0, e1))
     return out
 
 

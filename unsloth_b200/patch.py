@@ -1,0 +1,291 @@
+"""The monkey-patch surface: host-side mirror of the patched model forward of the reference
+(`unsloth/models/llama.py`: LlamaAttention_fast_forward :671-771, LlamaDecoderLayer_fast_forward
+:774-863, LlamaModel_fast_forward :866-1230, CausalLM_fast_forward :1370-1590; patch_peft_model
+:3599-3770; per-arch deltas `mistral.py:112-157`, `gemma2.py:104-283`).
+
+`install(model)` rebinds, per instance, exactly what Unsloth rebinds:
+    layer.mlp.forward          = MethodType(apply_lora_mlp_swiglu | apply_lora_mlp_geglu_approx, mlp)
+    layer.self_attn.apply_qkv  = apply_lora_qkv
+    layer.self_attn.apply_o    = apply_lora_o
+and replaces the forward of the attention / decoder-layer / model / CausalLM modules of a STOCK
+HuggingFace Llama / Mistral / Gemma-2 model with slim fast forwards that call the kernel API by
+name (fast_rms_layernorm, fast_rope_embedding, unsloth_fused_ce_loss).  The attention product
+itself is the external flash-attn library call, as in the reference
+(`unsloth/utils/attention_dispatch.py:433-617`).
+
+`build_qlora_model(...)` creates a random-init model of a named architecture directly on the GPU,
+NF4-quantises the seven projections of every layer (bitsandbytes-format statistics) and wraps
+them with LoRA -- what `FastLanguageModel.from_pretrained(load_in_4bit=True)` +
+`get_peft_model` produce, minus the hub.
+"""
+from __future__ import annotations
+
+import math
+import types
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from .lora import LoraLinear
+from .nf4 import Linear4bit
+from .packing import mask_packed_boundary_labels
+
+# model shapes of BASELINE.json configs (public model cards)
+CONFIGS = {
+    "llama-3.2-1b": dict(arch="llama", hidden_size=2048, num_hidden_layers=16, num_attention_heads=32,
+                         num_key_value_heads=8, head_dim=64, intermediate_size=8192, vocab_size=128256,
+                         rms_norm_eps=1e-5, rope_theta=500000.0, tie_word_embeddings=True,
+                         max_position_embeddings=131072,
+                         rope_scaling=dict(rope_type="llama3", factor=32.0, low_freq_factor=1.0,
+                                           high_freq_factor=4.0, original_max_position_embeddings=8192)),
+    "llama-3-8b": dict(arch="llama", hidden_size=4096, num_hidden_layers=32, num_attention_heads=32,
+                       num_key_value_heads=8, head_dim=128, intermediate_size=14336, vocab_size=128256,
+                       rms_norm_eps=1e-5, rope_theta=500000.0),
+    "mistral-7b-v0.3": dict(arch="mistral", hidden_size=4096, num_hidden_layers=32, num_attention_heads=32,
+                            num_key_value_heads=8, head_dim=128, intermediate_size=14336, vocab_size=32768,
+                            rms_norm_eps=1e-5, rope_theta=1000000.0, sliding_window=None),
+    "gemma-2-9b": dict(arch="gemma2", hidden_size=3584, num_hidden_layers=42, num_attention_heads=16,
+                       num_key_value_heads=8, head_dim=256, intermediate_size=14336, vocab_size=256000,
+                       rms_norm_eps=1e-6, rope_theta=10000.0, sliding_window=4096,
+                       attn_logit_softcapping=50.0, final_logit_softcapping=30.0,
+                       query_pre_attn_scalar=256),
+}
+
+
+# ---------------------------------------------------------------------------------------------
+# rotary tables (models/llama.py:1775-1914 LlamaRotaryEmbedding; gemma.py:247-319 fp32 tables)
+# ---------------------------------------------------------------------------------------------
+class RotaryCache:
+    """cos/sin tables [max_pos, D] (both halves duplicated), fp32 inv_freq, llama3 scaling; table
+    dtype = model dtype (Llama / Mistral) or fp32 (Gemma family), grown in steps of 8192."""
+
+    def __init__(self, head_dim, base, device, dtype, rope_scaling=None):
+        self.dim, self.base, self.device, self.dtype = head_dim, base, device, dtype
+        self.rope_scaling = rope_scaling
+        self.size = 0
+        self.cos = self.sin = None
+
+    def inv_freq(self):
+        inv = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.int64).float() / self.dim))
+        rs = self.rope_scaling
+        if rs and rs.get("rope_type", rs.get("type")) == "llama3":
+            factor, lo, hi = rs["factor"], rs["low_freq_factor"], rs["high_freq_factor"]
+            old = rs["original_max_position_embeddings"]
+            low_wl, high_wl = old / lo, old / hi
+            wl = 2 * math.pi / inv
+            scaled = torch.where(wl > low_wl, inv / factor, inv)
+            smooth = (old / wl - lo) / (hi - lo)
+            smoothed = (1 - smooth) / factor * inv + smooth * inv
+            mid = ~(wl < high_wl) * ~(wl > low_wl)
+            inv = torch.where(mid, smoothed, scaled)
+        return inv
+
+    def get(self, seq_len):
+        if seq_len > self.size:
+            self.size = ((seq_len + 8191) // 8192) * 8192
+            t = torch.arange(self.size, dtype=torch.float32)
+            freqs = torch.outer(t, self.inv_freq())
+            emb = torch.cat((freqs, freqs), dim=-1)
+            self.cos = emb.cos().to(device=self.device, dtype=self.dtype)
+            self.sin = emb.sin().to(device=self.device, dtype=self.dtype)
+        return self.cos, self.sin
+
+
+# ---------------------------------------------------------------------------------------------
+# fast forwards
+# ---------------------------------------------------------------------------------------------
+def _attention(Q, K_, V, scale, window, softcap):
+    """External library call, like the reference (attention_dispatch.py:452): causal flash-attn
+    on [B, S, H, D] views of the projection buffers (GQA native)."""
+    from flash_attn import flash_attn_func
+    return flash_attn_func(Q, K_, V, dropout_p=0.0, softmax_scale=scale, causal=True,
+                           window_size=window, softcap=softcap)
+
+
+def LlamaAttention_fast_forward(self, hidden_states, cos, sin, position_ids=None):
+    """models/llama.py:671-771 (training branch), mistral.py:61-157, gemma2.py:86-201."""
+    bsz, q_len, _ = hidden_states.size()
+    n_heads, n_kv, hd = self._ub_heads
+    Q, Kt, V = self.apply_qkv(self, hidden_states)                      # llama.py:702
+    Q = Q.view(bsz, q_len, n_heads, hd).transpose(1, 2)                 # views, no copies
+    Kt = Kt.view(bsz, q_len, n_kv, hd).transpose(1, 2)
+    Q, Kt = K.fast_rope_embedding(Q, Kt, cos, sin, position_ids)        # llama.py:730, in place
+    window = (-1, -1)
+    sw = self._ub_window
+    if sw is not None and q_len > sw:                                   # mistral.py:112-120
+        window = (sw, sw)
+    A = _attention(Q.transpose(1, 2), Kt.transpose(1, 2), V.view(bsz, q_len, n_kv, hd),
+                   self._ub_scale, window, self._ub_softcap)
+    return self.apply_o(self, A.reshape(bsz, q_len, n_heads * hd))      # llama.py:768
+
+
+def DecoderLayer_fast_forward(self, hidden_states, cos, sin, position_ids=None):
+    """models/llama.py:823-844 (Llama / Mistral) and gemma2.py:258-283 (four norms)."""
+    gemma = self._ub_gemma
+    residual = hidden_states
+    h = K.fast_rms_layernorm(self.input_layernorm, hidden_states, gemma=gemma)
+    h = LlamaAttention_fast_forward(self.self_attn, h, cos, sin, position_ids)
+    if gemma:
+        h = K.fast_rms_layernorm(self.post_attention_layernorm, h, gemma=True)
+    hidden_states = residual + h
+    residual = hidden_states
+    if gemma:
+        h = K.fast_rms_layernorm(self.pre_feedforward_layernorm, hidden_states, gemma=True)
+        h = self.mlp(h)
+        h = K.fast_rms_layernorm(self.post_feedforward_layernorm, h, gemma=True)
+    else:
+        h = K.fast_rms_layernorm(self.post_attention_layernorm, hidden_states)
+        h = self.mlp(h)
+    return residual + h
+
+
+def Model_fast_forward(self, input_ids, position_ids=None):
+    """models/llama.py:866-1230: embed, (Gemma: * sqrt(H) in model dtype :961-989), layers, norm."""
+    h = self.embed_tokens(input_ids)
+    if self._ub_gemma:
+        h = h * torch.tensor(math.sqrt(self.config.hidden_size), dtype=h.dtype, device=h.device)
+    seq_len = input_ids.shape[1]
+    need = seq_len
+    cos, sin = self._ub_rotary.get(need)
+    idx = None
+    if position_ids is not None:
+        idx = position_ids.reshape(-1).to(torch.int32)
+    for layer in self.layers:
+        h = DecoderLayer_fast_forward(layer, h, cos, sin, idx)
+    return K.fast_rms_layernorm(self.norm, h, gemma=self._ub_gemma)
+
+
+def CausalLM_fast_forward(self, input_ids=None, labels=None, position_ids=None,
+                          packed_seq_lengths=None, num_items_in_batch=None, **kwargs):
+    """models/llama.py:1371-1590, the `labels is not None and not UNSLOTH_RETURN_LOGITS` branch:
+    boundary-mask packed labels (:1483), logits-free fused CE (:1497-1509), EMPTY logits."""
+    hidden = Model_fast_forward(self.model, input_ids, position_ids)
+    if labels is None:
+        return SimpleNamespace(loss=None, logits=None, hidden_states=hidden)
+    labels = mask_packed_boundary_labels(labels, packed_seq_lengths)
+    loss = K.unsloth_fused_ce_loss(
+        trainer=None, hidden_states=hidden, lm_head_weight=self.lm_head.weight, lm_head_bias=None,
+        labels=labels, mask=None, n_items=num_items_in_batch, scaling=None, target_gb=None,
+        torch_compile=False, logit_softcapping=self._ub_final_softcap)
+    return SimpleNamespace(loss=loss, logits=None, hidden_states=None)
+
+
+# ---------------------------------------------------------------------------------------------
+# install: the per-instance rebinding of patch_peft_model (models/llama.py:3599-3770)
+# ---------------------------------------------------------------------------------------------
+def _arch_of(model):
+    mt = getattr(model.config, "model_type", "llama")
+    if mt not in ("llama", "mistral", "gemma2"):
+        raise NotImplementedError("unsloth_b200: model_type %r is outside the hot-path scope" % mt)
+    return mt
+
+
+def install(model):
+    """Rebind a HuggingFace Llama / Mistral / Gemma-2 CausalLM (with LoRA-wrapped projections)
+    onto the unsloth_b200 kernels.  Returns the model."""
+    arch = _arch_of(model)
+    cfg = model.config
+    gemma = arch == "gemma2"
+    inner = model.model
+    dev = inner.embed_tokens.weight.device
+    dtype = inner.embed_tokens.weight.dtype
+    hd = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+    rope_theta = getattr(cfg, "rope_theta", None)
+    rope_scaling = getattr(cfg, "rope_scaling", None)
+    rp = getattr(cfg, "rope_parameters", None)
+    if isinstance(rp, dict):
+        rope_theta = rp.get("rope_theta", rope_theta)
+        if rp.get("rope_type", "default") != "default":
+            rope_scaling = rp
+    inner._ub_rotary = RotaryCache(hd, float(rope_theta or 10000.0), dev,
+                                   torch.float32 if gemma else dtype, rope_scaling)
+    inner._ub_gemma = gemma
+    model._ub_final_softcap = float(getattr(cfg, "final_logit_softcapping", 0) or 0)
+    mlp_fn = K.apply_lora_mlp_geglu_approx if gemma else K.apply_lora_mlp_swiglu   # llama.py:3618-3639
+    for i, layer in enumerate(inner.layers):
+        attn = layer.self_attn
+        layer._ub_gemma = gemma
+        attn._ub_heads = (cfg.num_attention_heads, cfg.num_key_value_heads, hd)
+        if gemma:
+            attn._ub_scale = float(cfg.query_pre_attn_scalar) ** -0.5
+            attn._ub_softcap = float(getattr(cfg, "attn_logit_softcapping", 0) or 0)
+            attn._ub_window = cfg.sliding_window if i % 2 == 0 else None             # gemma2.py:139-150
+        else:
+            attn._ub_scale = hd ** -0.5
+            attn._ub_softcap = 0.0
+            attn._ub_window = getattr(cfg, "sliding_window", None) if arch == "mistral" else None
+        layer.mlp.forward = types.MethodType(mlp_fn, layer.mlp)                      # llama.py:3725
+        attn.apply_qkv = K.apply_lora_qkv                                            # llama.py:3748
+        attn.apply_o = K.apply_lora_o                                                # llama.py:3766
+    model.forward = types.MethodType(CausalLM_fast_forward, model)
+    return model
+
+
+def lora_parameters(model):
+    return [p for n, p in model.named_parameters() if ("lora_A" in n or "lora_B" in n)]
+
+
+TARGET_MODULES = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+
+
+def attach_qlora(model, r=16, lora_alpha=16, init_b_std=0.0, quantize=True):
+    """NF4-quantise (bitsandbytes layout) and LoRA-wrap the seven projections of every layer:
+    get_peft_model defaults of models/llama.py:3061-3075 (r=16, alpha=16, dropout 0, bias none)."""
+    for layer in model.model.layers:
+        for parent in (layer.self_attn, layer.mlp):
+            for name in TARGET_MODULES:
+                lin = getattr(parent, name, None)
+                if lin is None or isinstance(lin, LoraLinear):
+                    continue
+                if quantize:
+                    base = Linear4bit.from_dense(lin.weight.data)
+                else:
+                    base = lin
+                setattr(parent, name, LoraLinear(base, r=r, lora_alpha=lora_alpha,
+                                                 init_b_std=init_b_std))
+                del lin
+    for p in model.parameters():
+        p.requires_grad_(False)
+    for p in lora_parameters(model):
+        p.requires_grad_(True)
+    return model
+
+
+def hf_config(name, num_hidden_layers=None, **overrides):
+    spec = dict(CONFIGS[name])
+    spec.update(overrides)
+    arch = spec.pop("arch")
+    if num_hidden_layers is not None:
+        spec["num_hidden_layers"] = num_hidden_layers
+    spec.setdefault("max_position_embeddings", 8192)
+    spec["attention_bias"] = False
+    if arch == "llama":
+        from transformers import LlamaConfig as C
+        spec["mlp_bias"] = False
+    elif arch == "mistral":
+        from transformers import MistralConfig as C
+    else:
+        from transformers import Gemma2Config as C
+        spec["hidden_activation"] = "gelu_pytorch_tanh"
+    return C(**spec)
+
+
+def build_qlora_model(name="llama-3-8b", r=16, lora_alpha=16, device="cuda", dtype=torch.bfloat16,
+                      seed=3407, init_b_std=0.0, num_hidden_layers=None, quantize=True, **overrides):
+    """Random-init model of a BASELINE.json config on `device`, NF4 + LoRA, kernels installed."""
+    from transformers import AutoModelForCausalLM
+    cfg = hf_config(name, num_hidden_layers, **overrides)
+    torch.manual_seed(seed)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        with torch.device(device):
+            model = AutoModelForCausalLM.from_config(cfg)
+    finally:
+        torch.set_default_dtype(prev)
+    model.to(dtype)
+    attach_qlora(model, r=r, lora_alpha=lora_alpha, init_b_std=init_b_std, quantize=quantize)
+    torch.cuda.empty_cache()
+    return install(model)
