@@ -144,7 +144,8 @@ def cpu_reference_tokens_per_sec(model_name, seq_tokens, r=RANK_R, threads=None,
         for layer in m.model.layers:
             for parent in (layer.self_attn, layer.mlp):
                 for nme in ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"):
-                    setattr(parent, nme, PlainLoRA(getattr(parent, nme), r, r))
+                    if hasattr(parent, nme):
+                        setattr(parent, nme, PlainLoRA(getattr(parent, nme), r, r))
         ids = torch.randint(0, cfg.vocab_size, (1, seq_tokens))
         best = None
         t_begin = time.perf_counter()
