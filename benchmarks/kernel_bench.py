@@ -120,6 +120,7 @@ def main():
             C = torch.empty(M, Nn, device=DEV, dtype=BF)
             fl = 2.0 * M * Nn * Kk
             report("gemm_kk_" + name, timeit(lambda: K.gemm(M, Nn, [(A, B, Kk)], C), flush=False), flops=fl, M=M, N=Nn, K=Kk)
+            report("gemm_kk_1cta_" + name, timeit(lambda: K.gemm(M, Nn, [(A, B, Kk)], C, cta_group=1), flush=False), flops=fl)
             report("cublas_" + name, timeit(lambda: torch.matmul(A, B.t(), out=C), flush=False), flops=fl)
             Bt = B.t().contiguous()
             report("gemm_kmn_" + name, timeit(lambda: K.gemm(M, Nn, [(A, Bt, Kk)], C, b_mn=True), flush=False), flops=fl)

@@ -132,7 +132,9 @@ void cdequantize_blockwise_fp16_nf4(float* code, unsigned char* A, float* absmax
  *   b_mn_major == 0: B_s is row-major [N, K_s] (ldb);  != 0: B_s is row-major [K_s, N].
  * Operands bf16 (or fp16), 16-byte aligned, ld multiple of 8.  C: bf16/fp16/fp32, ldc elements.
  * split_k > 1 needs `workspace` of ub200_gemm_workspace_bytes(); reduction order is fixed
- * (deterministic).  block_n: 0 = auto, or 64 / 128 / 256.                                      */
+ * (deterministic).  block_n: 0 = auto, or 64 / 128 / 256.  cta_group: 0 = auto, 1 = one CTA
+ * per 128 x block_n tile, 2 = CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x block_n
+ * tile (block_n >= 128).                                                                       */
 typedef struct {
   const void* a;
   int64_t lda;
@@ -142,7 +144,8 @@ typedef struct {
 } ub200_gemm_segment;
 int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
                int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype, float alpha,
-               int accumulate, int split_k, void* workspace, int block_n, cudaStream_t stream);
+               int accumulate, int split_k, void* workspace, int block_n, int cta_group,
+               cudaStream_t stream);
 int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* bytes);
 
 /* ---- small helpers of the LoRA path ---------------------------------------------------------

@@ -25,9 +25,12 @@ def rel_err(a, b):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("M,N,K,bn", [(256, 512, 256, 0), (304, 200, 136, 0), (128, 64, 8192, 64),
-                                      (640, 384, 1000, 128), (1024, 1024, 512, 256)])
-def test_gemm_layouts(a_mn, b_mn, M, N, K, bn):
+@pytest.mark.parametrize("M,N,K,bn,cg", [(256, 512, 256, 0, 1), (304, 200, 136, 0, 1), (128, 64, 8192, 64, 1),
+                                         (640, 384, 1000, 128, 1), (1024, 1024, 512, 256, 1),
+                                         (256, 512, 256, 256, 2), (304, 200, 136, 128, 2),
+                                         (640, 384, 1000, 128, 2), (1024, 1024, 512, 256, 2),
+                                         (2048, 1536, 4096, 256, 2), (136, 264, 72, 0, 0)])
+def test_gemm_layouts(a_mn, b_mn, M, N, K, bn, cg):
     from unsloth_b200.kernels import gemm
     torch.manual_seed(M + N + K)
     A = torch.randn(M, K, device=DEV).to(BF)
@@ -36,10 +39,10 @@ def test_gemm_layouts(a_mn, b_mn, M, N, K, bn):
     Aop = A.t().contiguous() if a_mn else A
     Bop = B.t().contiguous() if b_mn else B
     out32 = torch.empty(M, N, device=DEV, dtype=torch.float32)
-    gemm(M, N, [(Aop, Bop, K)], out32, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+    gemm(M, N, [(Aop, Bop, K)], out32, a_mn=a_mn, b_mn=b_mn, block_n=bn, cta_group=cg)
     assert rel_err(out32, ref) < 2e-3, rel_err(out32, ref)
     out16 = torch.empty(M, N, device=DEV, dtype=BF)
-    gemm(M, N, [(Aop, Bop, K)], out16, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+    gemm(M, N, [(Aop, Bop, K)], out16, a_mn=a_mn, b_mn=b_mn, block_n=bn, cta_group=cg)
     assert rel_err(out16, ref) < 6e-3
 
 
@@ -51,9 +54,14 @@ def test_gemm_segments_alpha_accumulate_splitk():
     As = [torch.randn(M, k, device=DEV).to(BF) for k in Ks]
     Bs = [torch.randn(N, k, device=DEV).to(BF) for k in Ks]
     ref = sum(a.float() @ b.float().t() for a, b in zip(As, Bs))
-    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
-    gemm(M, N, [(a, b, k) for a, b, k in zip(As, Bs, Ks)], out)
-    assert rel_err(out, ref) < 2e-3
+    for cg in (1, 2):
+        out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        gemm(M, N, [(a, b, k) for a, b, k in zip(As, Bs, Ks)], out, cta_group=cg, block_n=128)
+        assert rel_err(out, ref) < 2e-3
+        # split-K through the CTA-pair kernel as well
+        out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        gemm(M, N, [(a, b, k) for a, b, k in zip(As, Bs, Ks)], out, cta_group=cg, block_n=128, split_k=3)
+        assert rel_err(out, ref) < 2e-3
     # alpha + accumulate into an existing bf16 C
     C0 = torch.randn(M, N, device=DEV).to(BF)
     C = C0.clone()

@@ -64,7 +64,7 @@ _SIGS = {
     "cdequantize_blockwise_bf16_nf4": ([_p, _p, _p, _p, _i, _i, _p], None),
     "cdequantize_blockwise_fp16_nf4": ([_p, _p, _p, _p, _i, _i, _p], None),
     "ub200_gemm": ([_i, _i, POINTER(GemmSegment), _i, _i, _i, _i, _p, _l, _i, _f, _i, _i, _p, _i,
-                    _p], c_int),
+                    _i, _p], c_int),
     "ub200_gemm_workspace_bytes": ([_i, _i, _i, POINTER(c_int64)], c_int),
     "ub200_cast_pad_2d": ([_p, _i, _l, _i, _i, _p, _i, _l, _i, _i, _i, _i, _f, _i, _p], c_int),
     "ub200_adamw_flat": ([_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _f, _p], c_int),

@@ -160,6 +160,66 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------
+// cta_group::2 (CTA-pair) variants
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs issue their loads; transaction bytes are credited to the LEADER's barrier
+// (peer bit cleared, cute::Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout; 128B swizzle everywhere)
 //   K-major  tile: rows of 64 elements (128 B); 8-row groups 1024 B apart        -> SBO=1024
 //   MN-major tile: [64 k-rows x 64 mn] boxes of 8 KB; 8-k-row groups 1024 B apart -> SBO=1024,
@@ -185,6 +245,73 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn,
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;
+}
+
+// Epilogue store of 32 consecutive accumulator columns of one row: alpha, optional beta=1
+// read-modify-write, conversion to the output dtype, 16-byte global stores.
+__device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&r)[32], bool has_k,
+                                            int row, int col0, int sp) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * p.alpha : 0.f;
+  const bool full = (col0 + 32 <= p.N);
+  if (p.c_dtype == UB200_F32) {
+    float* cptr = reinterpret_cast<float*>(p.C) + (int64_t)sp * p.split_stride +
+                  (int64_t)row * p.ldc + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(cptr + i);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(cptr + i) = o;
+      }
+    } else {
+      for (int i = 0; i < 32 && col0 + i < p.N; ++i)
+        cptr[i] = p.accumulate ? cptr[i] + v[i] : v[i];
+    }
+  } else {
+    // 16-bit output (bf16 / fp16)
+    uint16_t* cptr = reinterpret_cast<uint16_t*>(p.C) + (int64_t)row * p.ldc + col0;
+    const bool bf = p.c_dtype == UB200_BF16;
+    if (full && ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o;
+        if (p.accumulate) {
+          const uint4 old = *reinterpret_cast<const uint4*>(cptr + i);
+          const uint16_t* oh = reinterpret_cast<const uint16_t*>(&old);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[i + j] += bf ? __bfloat162float(__ushort_as_bfloat16(oh[j]))
+                           : __half2float(__ushort_as_half(oh[j]));
+        }
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (bf) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+            ow[j] = *reinterpret_cast<uint32_t*>(&t);
+          } else {
+            __half2 t = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+            ow[j] = *reinterpret_cast<uint32_t*>(&t);
+          }
+        }
+        *reinterpret_cast<uint4*>(cptr + i) = o;
+      }
+    } else {
+      for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
+        float val = v[i];
+        if (p.accumulate)
+          val += bf ? __bfloat162float(__ushort_as_bfloat16(cptr[i]))
+                    : __half2float(__ushort_as_half(cptr[i]));
+        cptr[i] = bf ? __bfloat16_as_ushort(__float2bfloat16_rn(val))
+                     : __half_as_ushort(__float2half_rn(val));
+      }
+    }
+  }
 }
 
 template <int BLOCK_N>
@@ -350,69 +477,7 @@ gemm_kernel(const __grid_constant__ Params p) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
         tmem_ld32(taddr, r);
         tmem_ld_wait(r);
-        if (row_ok) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = has_k ? __uint_as_float(r[i]) * p.alpha : 0.f;
-          const bool full = (col0 + 32 <= p.N);
-          if (p.c_dtype == UB200_F32) {
-            float* cptr = reinterpret_cast<float*>(p.C) + (int64_t)sp * p.split_stride +
-                          (int64_t)row * p.ldc + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (p.accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(cptr + i);
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(cptr + i) = o;
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i)
-                cptr[i] = p.accumulate ? cptr[i] + v[i] : v[i];
-            }
-          } else {
-            // 16-bit output (bf16 / fp16)
-            uint16_t* cptr = reinterpret_cast<uint16_t*>(p.C) + (int64_t)row * p.ldc + col0;
-            const bool bf = p.c_dtype == UB200_BF16;
-            if (full && ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 o;
-                if (p.accumulate) {
-                  const uint4 old = *reinterpret_cast<const uint4*>(cptr + i);
-                  const uint16_t* oh = reinterpret_cast<const uint16_t*>(&old);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    v[i + j] += bf ? __bfloat162float(__ushort_as_bfloat16(oh[j]))
-                                   : __half2float(__ushort_as_half(oh[j]));
-                }
-                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (bf) {
-                    __nv_bfloat162 t = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-                    ow[j] = *reinterpret_cast<uint32_t*>(&t);
-                  } else {
-                    __half2 t = __floats2half2_rn(v[i + 2 * j], v[i + 2 * j + 1]);
-                    ow[j] = *reinterpret_cast<uint32_t*>(&t);
-                  }
-                }
-                *reinterpret_cast<uint4*>(cptr + i) = o;
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
-                float val = v[i];
-                if (p.accumulate)
-                  val += bf ? __bfloat162float(__ushort_as_bfloat16(cptr[i]))
-                            : __half2float(__ushort_as_half(cptr[i]));
-                cptr[i] = bf ? __bfloat16_as_ushort(__float2bfloat16_rn(val))
-                             : __half_as_ushort(__float2half_rn(val));
-              }
-            }
-          }
-        }
+        if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
       }
       // release the accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -427,6 +492,200 @@ gemm_kernel(const __grid_constant__ Params p) {
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// CTA-pair kernel: cluster (2,1,1), tcgen05 cta_group::2, pair tile 256 (M) x BLOCK_N.
+// Each CTA stages its own 128 rows of A and its own half (BLOCK_N/2 rows) of B, so the pair
+// moves (256 + BLOCK_N) x 64 operand elements per k-block for a 256 x BLOCK_N x 64 MMA: 1.5x
+// fewer L2->SMEM bytes per flop than the single-CTA 128 x 256 tile, which the ncu capture of
+// round 1 showed to be the limiter (profiles/gemm_r1_summary.md).  The leader CTA's elected
+// thread issues the MMAs for both SMs; tcgen05.commit multicasts the stage-free and
+// accumulator-ready arrivals to both CTAs; each CTA's epilogue drains its own 128 TMEM lanes.
+// ---------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int HALF_N = BLOCK_N / 2;
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB (this CTA's 128 rows)
+  static constexpr uint32_t B_BYTES = HALF_N * BLOCK_K * 2;    // this CTA's half of B
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;           // double-buffered accumulator
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ Params p) {
+  using C = Cfg2<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8u * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();      // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  int total_kb = 0;
+  for (int s = 0; s < p.n_segs; ++s) total_kb += p.seg_kblocks[s];
+  const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_tiles = m_pairs * p.n_tiles;
+  const int num_work = num_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.n_segs; ++s) { prefetch_tmap(&p.tmap_a[s]); prefetch_tmap(&p.tmap_b[s]); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      // full: leader's own arrive.expect_tx + the peer producer's remote arrive
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+      // tmem_empty (leader's copy is the one used): 4 epilogue warps x 2 CTAs
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(tmem_ptr_smem, C::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  auto work_range = [&](int w, int& tile, int& kb0, int& kb1) {
+    tile = w % num_tiles;
+    const int sp = w / num_tiles;
+    const int per = (total_kb + p.split_k - 1) / p.split_k;
+    kb0 = sp * per;
+    kb1 = min(total_kb, kb0 + per);
+  };
+  auto tile_coords = [&](int tile, int& m_pair, int& n_blk) {
+    m_pair = tile % m_pairs;
+    n_blk = tile / m_pairs;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair; w < num_work; w += num_pairs) {
+        int tile, kb0, kb1, m_pair, n_blk;
+        work_range(w, tile, kb0, kb1);
+        tile_coords(tile, m_pair, n_blk);
+        const int m0 = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M;     // this CTA's A rows
+        const int n0 = n_blk * BLOCK_N + (int)rank * C::HALF_N;         // this CTA's B rows
+        int seg = 0, seg_start = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          while (kb >= seg_start + p.seg_kblocks[seg]) { seg_start += p.seg_kblocks[seg]; ++seg; }
+          const int k0 = (kb - seg_start) * BLOCK_K;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
+          else mbar_arrive_remote(full_bar(stage), 0u);
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &p.tmap_a[seg], full_bar(stage), k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d_2sm(sa + j * 8192u, &p.tmap_a[seg], full_bar(stage), m0 + j * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &p.tmap_b[seg], full_bar(stage), k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < C::HALF_N / 64; ++j)
+              tma_load_2d_2sm(sb + j * 8192u, &p.tmap_b[seg], full_bar(stage), n0 + j * 64, k0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ===================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N, p.a_mn, p.b_mn, p.ab_fp16);
+      const uint32_t a_adv = p.a_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
+      const uint32_t b_adv = p.b_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = pair; w < num_work; w += num_pairs) {
+        int tile, kb0, kb1;
+        work_range(w, tile, kb0, kb1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = make_smem_desc(sa, a_lbo, 1024u);
+          const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(empty_bar(stage));      // frees the stage in BOTH CTAs
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));          // accumulator ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs, own 128 lanes) ============
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = pair; w < num_work; w += num_pairs) {
+      int tile, kb0, kb1, m_pair, n_blk;
+      work_range(w, tile, kb0, kb1);
+      tile_coords(tile, m_pair, n_blk);
+      const int sp = w / num_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool has_k = kb1 > kb0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        const int col0 = n_blk * BLOCK_N + c;
+        if (col0 >= p.N) break;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
+        tmem_ld32(taddr, r);
+        tmem_ld_wait(r);
+        if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0u);   // leader's barrier
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -509,6 +768,20 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
   return UB200_OK;
 }
 
+template <int BLOCK_N>
+static int launch2(const Params& p, int grid, cudaStream_t st) {
+  using C = Cfg2<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  gemm2_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);   // __cluster_dims__(2,1,1)
+  return UB200_OK;
+}
+
 }  // namespace gemm
 }  // namespace ub
 
@@ -521,7 +794,7 @@ extern "C" int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* by
 extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
                           int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype,
                           float alpha, int accumulate, int split_k, void* workspace,
-                          int block_n, cudaStream_t stream) {
+                          int block_n, int cta_group, cudaStream_t stream) {
   using namespace ub;
   using namespace ub::gemm;
   if (M <= 0 || N <= 0) return UB200_OK;
@@ -532,6 +805,10 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
   int bn = block_n;
   if (bn == 0) bn = (N >= 256 || N > 128) ? 256 : (N > 64 ? 128 : 64);
   if (bn != 256 && bn != 128 && bn != 64) return UB200_ERR_BAD_ARG;
+  if (cta_group != 0 && cta_group != 1 && cta_group != 2) return UB200_ERR_BAD_ARG;
+  // CTA pairs pay off when the tile grid is large; the skinny rank-block GEMMs stay single-CTA
+  bool pair = cta_group == 2 || (cta_group == 0 && bn >= 128 && M > BLOCK_M);
+  if (pair && bn < 128) return UB200_ERR_BAD_ARG;
 
   Params p;
   memset(&p, 0, sizeof(p));
@@ -553,7 +830,7 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     if (!p.a_mn) rc = make_tmap(&p.tmap_a[s], g.a, M, g.k, g.lda, BLOCK_M, p.ab_fp16);
     else         rc = make_tmap(&p.tmap_a[s], g.a, g.k, M, g.lda, 64, p.ab_fp16);
     if (rc) return rc;
-    if (!p.b_mn) rc = make_tmap(&p.tmap_b[s], g.b, N, g.k, g.ldb, bn, p.ab_fp16);
+    if (!p.b_mn) rc = make_tmap(&p.tmap_b[s], g.b, N, g.k, g.ldb, pair ? bn / 2 : bn, p.ab_fp16);
     else         rc = make_tmap(&p.tmap_b[s], g.b, g.k, N, g.ldb, 64, p.ab_fp16);
     if (rc) return rc;
   }
@@ -573,12 +850,19 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     p.c_dtype = c_dtype;
     p.accumulate = accumulate;
   }
-  const int num_work = p.m_tiles * p.n_tiles * split_k;
-  const int grid = num_work < UB_SM_COUNT ? num_work : UB_SM_COUNT;
   int rc;
-  if (bn == 256) rc = launch<256>(p, grid, stream);
-  else if (bn == 128) rc = launch<128>(p, grid, stream);
-  else rc = launch<64>(p, grid, stream);
+  if (pair) {
+    const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const int num_work = m_pairs * p.n_tiles * split_k;
+    int pairs = num_work < UB_SM_COUNT / 2 ? num_work : UB_SM_COUNT / 2;
+    rc = bn == 256 ? launch2<256>(p, 2 * pairs, stream) : launch2<128>(p, 2 * pairs, stream);
+  } else {
+    const int num_work = p.m_tiles * p.n_tiles * split_k;
+    const int grid = num_work < UB_SM_COUNT ? num_work : UB_SM_COUNT;
+    if (bn == 256) rc = launch<256>(p, grid, stream);
+    else if (bn == 128) rc = launch<128>(p, grid, stream);
+    else rc = launch<64>(p, grid, stream);
+  }
   if (rc) return rc;
   if (split_k > 1) {
     const int64_t total = (int64_t)M * N;

@@ -86,7 +86,7 @@ GEMM_EVENTS = None
 
 
 def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, split_k=1,
-         block_n=0):
+         block_n=0, cta_group=0):
     """out[M,N] (+)= alpha * sum_s A_s . B_s^T on the tcgen05 tensor cores.
 
     segs: list of (A, B, K).  a_mn=False: A is [M, K]; True: A is [K, M] (row-major).
@@ -110,7 +110,7 @@ def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, s
         e0.record()
     L.call("ub200_gemm", M, N, arr, n, int(a_mn), int(b_mn), L.dt(ab_dtype), L.ptr(out),
            out.stride(0), L.dt(out), float(alpha), int(accumulate), int(split_k), L.ptr(ws),
-           int(block_n), L.stream())
+           int(block_n), int(cta_group), L.stream())
     if ev is not None:
         e1.record()
         ev.append((2.0 * M * N * sum(k for _, _, k in segs), e0, e1))
