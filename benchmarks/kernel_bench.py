@@ -130,7 +130,21 @@ def main():
         o = torch.empty(4096, 64, device=DEV, dtype=torch.float32)
         report("gemm_mnmn_dA", timeit(lambda: K.gemm(4096, 64, [(X, G, T)], o, a_mn=True, b_mn=True, split_k=4)),
                bytes_=T * 4096 * 2 + T * 64 * 2, flops=2.0 * T * 4096 * 64)
+        for sk in (1, 2, 4, 8, 16):
+            report("gemm_mnmn_dA_split%d" % sk, timeit(lambda: K.gemm(4096, 64, [(X, G, T)], o, a_mn=True, b_mn=True, split_k=sk)),
+                   bytes_=T * 4096 * 2 + T * 64 * 2)
         A64 = torch.randn(64, 4096, device=DEV, dtype=BF); XA = torch.empty(T, 64, device=DEV, dtype=BF)
+        for sk in (1, 2, 4):
+            report("gemm_xa_skinny_split%d" % sk, timeit(lambda: K.gemm(T, 64, [(X, A64, 4096)], XA, split_k=sk)),
+                   bytes_=T * 4096 * 2 + T * 64 * 2)
+        big = torch.randn(T, I, device=DEV, dtype=BF); A64b = torch.randn(64, I, device=DEV, dtype=BF)
+        for sk in (1, 2, 4):
+            report("gemm_xa_skinny_K14336_split%d" % sk, timeit(lambda: K.gemm(T, 64, [(big, A64b, I)], XA, split_k=sk)),
+                   bytes_=T * I * 2 + T * 64 * 2)
+        o2 = torch.empty(I, 64, device=DEV, dtype=torch.float32)
+        for sk in (1, 2, 4):
+            report("gemm_mnmn_dB_M14336_split%d" % sk, timeit(lambda: K.gemm(I, 64, [(big, G, T)], o2, a_mn=True, b_mn=True, split_k=sk)),
+                   bytes_=T * I * 2 + T * 64 * 2)
         report("gemm_xa_skinny", timeit(lambda: K.gemm(T, 64, [(X, A64, 4096)], XA)), bytes_=T * 4096 * 2 + T * 64 * 2,
                flops=2.0 * T * 4096 * 64)
 

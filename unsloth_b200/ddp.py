@@ -87,5 +87,7 @@ class FlatLoRABucket:
                    L.ptr(self.v), self.flat_p.numel(), float(self.lr), float(b1), float(b2),
                    float(self.eps), float(self.wd), 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, float(gs),
                    L.stream())
+            from .kernels.utils import bump_param_epoch
+            bump_param_epoch()      # invalidate the per-step LoRA cast cache
         else:
             raise RuntimeError("unsloth_b200: the optimiser step runs only on CUDA (no CPU fallback)")

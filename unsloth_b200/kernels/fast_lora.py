@@ -20,13 +20,18 @@ from __future__ import annotations
 import torch
 
 from .. import _lib as L
-from .utils import (RANK_BLOCK, as_b_operand, cast_pad, dense_weight, gemm,
+from .utils import (RANK_BLOCK, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
                     get_lora_parameters, get_lora_parameters_bias, matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
 from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
                     geglu_approx_forward_kernel, geglu_approx_backward_kernel)
 
 _SM = 148
+
+
+def _epoch():
+    from . import utils as _u
+    return _u.PARAM_EPOCH
 
 
 def _as2d(t):
@@ -51,6 +56,15 @@ class _Group:
         self.T, self.in_f = X2.shape
         self.dtype = X2.dtype
         self.dev = X2.device
+        self._init_ranks()
+
+    def drop_input(self):
+        """Keep only what the backward needs from the parameters (not the activation)."""
+        self.X2 = None
+        return self
+
+    def _init_ranks(self):
+        projs = self.projs
         self.offs, off = [], 0
         for (_, _, A, _, _) in projs:
             self.offs.append(off)
@@ -63,12 +77,30 @@ class _Group:
     # [Rp, in] : rows offs[i].. hold A_i in the compute dtype, zero elsewhere
     def A_cat(self):
         if self._A_cat is None:
-            A_cat = torch.empty((self.Rp, self.in_f), dtype=self.dtype, device=self.dev)
             blocks = [(o, A) for o, (_, _, A, _, _) in zip(self.offs, self.projs) if A is not None]
+            if len(blocks) == 1 and blocks[0][0] == 0:
+                A = blocks[0][1]
+                A = A if A.stride(-1) == 1 else A.contiguous()
+                self._A_cat = cached_cast_pad(A, (self.Rp, self.in_f), self.dtype)
+                return self._A_cat
+            # several adapters share the rank block: memoise on the first adapter's Parameter,
+            # keyed by the versions of all of them
+            first = blocks[0][1]
+            ver = tuple((A._version, A.data_ptr()) for _, A in blocks) + (_epoch(),)
+            cache = first.__dict__.setdefault("_ub200_acat_cache", {}) if isinstance(first, torch.nn.Parameter) else None
+            key = (self.Rp, self.in_f, self.dtype, tuple(o for o, _ in blocks))
+            if cache is not None:
+                hit = cache.get(key)
+                if hit is not None and hit[0] == ver:
+                    self._A_cat = hit[1]
+                    return self._A_cat
+            A_cat = torch.empty((self.Rp, self.in_f), dtype=self.dtype, device=self.dev)
             for j, (o, A) in enumerate(blocks):
                 end = blocks[j + 1][0] if j + 1 < len(blocks) else self.Rp
                 A = A if A.stride(-1) == 1 else A.contiguous()
                 cast_pad(A, A_cat[o:end])
+            if cache is not None:
+                cache[key] = (ver, A_cat)
             self._A_cat = A_cat
         return self._A_cat
 
@@ -88,11 +120,9 @@ class _Group:
             if A is not None:
                 Bc = B if B.stride(-1) == 1 else B.contiguous()
                 if b_mn:
-                    B_pad = cast_pad(Bc, torch.empty((self.Rp, N), dtype=dt, device=dev),
-                                     row_off=off, scale=s, transpose=True)
+                    B_pad = cached_cast_pad(Bc, (self.Rp, N), dt, row_off=off, scale=s, transpose=True)
                 else:
-                    B_pad = cast_pad(Bc, torch.empty((N, self.Rp), dtype=dt, device=dev),
-                                     col_off=off, scale=s)
+                    B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s)
                 segs.append((XA, B_pad, self.Rp))
             Y = torch.empty((T, N), dtype=dt, device=dev)
             gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
@@ -112,8 +142,7 @@ class _Group:
                     continue
                 Bc = B if B.stride(-1) == 1 else B.contiguous()
                 out_f = Bc.shape[0]
-                BT_pad = cast_pad(Bc, torch.empty((Rp, out_f), dtype=dt, device=dev),
-                                  row_off=off, scale=s, transpose=True)
+                BT_pad = cached_cast_pad(Bc, (Rp, out_f), dt, row_off=off, scale=s, transpose=True)
                 segs.append((dY, BT_pad, out_f))
             G = gemm(T, Rp, segs, torch.empty((T, Rp), dtype=dt, device=dev))
             # dA_cat^T [in, Rp] = X^T @ G   (both operands MN-major, reduction over tokens)
@@ -172,7 +201,10 @@ class LoRA_MLP(torch.autograd.Function):
         (i,), XA2 = grp2.forward()
         ctx.custom_saved_tensors = (gateW, gateW_quant, gateS, upW, upW_quant, upS, downW,
                                     downW_quant, downS, _backward_function)
-        ctx.save_for_backward(gateA, gateB, upA, upB, downA, downB, X2, e, g, XA1, XA2)
+        # LoRA A/B are kept as the caller's Parameter objects (not through save_for_backward) so
+        # that the per-step cast cache, which lives on the Parameter, is hit in backward as well
+        ctx.lora = (gateA, gateB, upA, upB, downA, downB)
+        ctx.save_for_backward(X2, e, g, XA1, XA2)
         ctx.inplace = inplace
         ctx.shape = shape
         return i.view(*b_s, -1)
@@ -182,7 +214,8 @@ class LoRA_MLP(torch.autograd.Function):
     def backward(ctx, dY):
         (gateW, gateW_quant, gateS, upW, upW_quant, upS, downW, downW_quant, downS,
          _backward_function) = ctx.custom_saved_tensors
-        gateA, gateB, upA, upB, downA, downB, X2, e, g, XA1, XA2 = ctx.saved_tensors
+        gateA, gateB, upA, upB, downA, downB = ctx.lora
+        X2, e, g, XA1, XA2 = ctx.saved_tensors
         dY2 = _as2d(dY)
         T = X2.shape[0]
         dt, dev = X2.dtype, X2.device
@@ -198,8 +231,7 @@ class LoRA_MLP(torch.autograd.Function):
         segs.append((dY2, Bop, dY2.shape[1]))
         if downA is not None:
             Bc = downB if downB.stride(-1) == 1 else downB.contiguous()
-            BT_pad = cast_pad(Bc, torch.empty((down.Rp, Bc.shape[0]), dtype=dt, device=dev),
-                              scale=downS, transpose=True)
+            BT_pad = cached_cast_pad(Bc, (down.Rp, Bc.shape[0]), dt, scale=downS, transpose=True)
             G_down = gemm(T, down.Rp, [(dY2, BT_pad, Bc.shape[0])],
                           torch.empty((T, down.Rp), dtype=dt, device=dev))
             segs.append((G_down, down.A_cat(), down.Rp))
@@ -274,7 +306,8 @@ class LoRA_QKV(torch.autograd.Function):
         if len(shape) == 3:
             Q, K, V = (t.view(shape[0], shape[1], -1) for t in (Q, K, V))
         ctx.custom_saved_tensors = (QW, QW_quant, QS, KW, KW_quant, KS, VW, VW_quant, VS)
-        ctx.save_for_backward(X2, QA, QB, KA, KB, VA, VB, XA)
+        ctx.lora = (QA, QB, KA, KB, VA, VB)
+        ctx.save_for_backward(X2, XA)
         ctx.inplace = inplace
         ctx.shape = shape
         return Q, K, V
@@ -283,7 +316,8 @@ class LoRA_QKV(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dQ, dK, dV):
         QW, QW_quant, QS, KW, KW_quant, KS, VW, VW_quant, VS = ctx.custom_saved_tensors
-        X2, QA, QB, KA, KB, VA, VB, XA = ctx.saved_tensors
+        QA, QB, KA, KB, VA, VB = ctx.lora
+        X2, XA = ctx.saved_tensors
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
                           (VW, VW_quant, VA, VB, VS)])
         dX, ((dQA, dQB), (dKA, dKB), (dVA, dVB)) = grp.backward(
@@ -313,7 +347,8 @@ class LoRA_W(torch.autograd.Function):
         grp = _Group(X2, [(W, W_quant, A, B, S)])
         (XW,), XA = grp.forward()
         ctx.custom_saved_tensors = (W, W_quant, S)
-        ctx.save_for_backward(A, B, X2, XA)
+        ctx.lora = (A, B)
+        ctx.save_for_backward(X2, XA)
         ctx.shape = shape
         return XW.view(*shape[:-1], -1)
 
@@ -321,7 +356,8 @@ class LoRA_W(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dY):
         W, W_quant, S = ctx.custom_saved_tensors
-        A, B, X2, XA = ctx.saved_tensors
+        A, B = ctx.lora
+        X2, XA = ctx.saved_tensors
         grp = _Group(X2, [(W, W_quant, A, B, S)])
         dX, ((dA, dB),) = grp.backward([_as2d(dY)], XA)
         return dX.view(ctx.shape), None, None, dA, dB, None

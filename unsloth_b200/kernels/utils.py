@@ -126,6 +126,34 @@ def cast_pad(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
     return dst
 
 
+# Parameters updated behind autograd's back (ub200_adamw_flat writes through raw pointers and does
+# not bump tensor._version) bump this epoch so cached casts are rebuilt.
+PARAM_EPOCH = 0
+
+
+def bump_param_epoch():
+    global PARAM_EPOCH
+    PARAM_EPOCH += 1
+
+
+def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpose=False):
+    """`cast_pad` into a fresh [shape] tensor, memoised ON the source nn.Parameter (LoRA A / B
+    change once per optimiser step, not once per call).  Non-Parameter sources are never cached."""
+    if not isinstance(src, torch.nn.Parameter):
+        return cast_pad(src, torch.empty(shape, dtype=dtype, device=src.device), row_off, col_off,
+                        scale, transpose)
+    cache = src.__dict__.setdefault("_ub200_cast_cache", {})
+    key = (tuple(shape), dtype, row_off, col_off, float(scale), bool(transpose))
+    ver = (src._version, PARAM_EPOCH, src.data_ptr())
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    dst = cast_pad(src, torch.empty(shape, dtype=dtype, device=src.device), row_off, col_off, scale,
+                   transpose)
+    cache[key] = (ver, dst)
+    return dst
+
+
 def dense_weight(W, W_quant, dtype, slot=0):
     """Logical [N_out, K_in] weight in the compute dtype, exactly what the reference's
     `fast_dequantize(W, W_quant)` hands to `torch.matmul(X, W.t())`: a reusable-slot dequantised
