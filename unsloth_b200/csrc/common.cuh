@@ -85,6 +85,42 @@ __device__ __forceinline__ float load_as_f(const void* p, int dt, int64_t i) {
   return reinterpret_cast<const float*>(p)[i];
 }
 
+// V consecutive weights/table entries starting at element `i0` (multiple of V) as floats.  One
+// 16-byte (or two, for fp32 tables feeding 16-bit activations) vector load when alignment allows.
+template <int V>
+__device__ __forceinline__ void load_vec_as_f(const void* p, int dt, int64_t i0, float (&out)[V]) {
+  if (dt == UB200_F32) {
+    const float* f = reinterpret_cast<const float*>(p) + i0;
+    if ((reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < V / 4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(f)[q];
+        out[4 * q] = t.x; out[4 * q + 1] = t.y; out[4 * q + 2] = t.z; out[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) out[i] = f[i];
+    }
+  } else {
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(p) + i0;
+    uint16_t raw[V];
+    if (V == 8 && (reinterpret_cast<uintptr_t>(h) & 15) == 0) {
+      const uint4 t = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(raw) = t;
+    } else if (V == 4 && (reinterpret_cast<uintptr_t>(h) & 7) == 0) {
+      const uint2 t = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(raw) = t;
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) raw[i] = h[i];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      out[i] = dt == UB200_BF16 ? __bfloat162float(__ushort_as_bfloat16(raw[i]))
+                                : __half2float(__ushort_as_half(raw[i]));
+  }
+}
+
 // ---- reductions ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

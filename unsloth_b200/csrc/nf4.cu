@@ -42,9 +42,12 @@ __global__ void __launch_bounds__(256) dequant_nf4_kernel(
     const uint8_t* __restrict__ absmax_q, const float* __restrict__ code2,
     const float* __restrict__ absmax2, const float* __restrict__ offset, T* __restrict__ out,
     int64_t n, int blocksize, int blocksize2) {
-  __shared__ float lut[16];
-  if (threadIdx.x < 16) lut[threadIdx.x] = kNF4[threadIdx.x];
+  // one private copy of the 16-entry code book per shared-memory bank (entry q of lane l at
+  // word q*32 + l): every lookup is conflict free whatever the nibble pattern
+  __shared__ float lut_b[16 * 32];
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) lut_b[i] = kNF4[i >> 5];
   __syncthreads();
+  const float* lut = lut_b + (threadIdx.x & 31);
   const float off = offset ? *offset : 0.f;
   auto absmax_of = [&](int64_t e) {
     const int64_t blk = e / blocksize;
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(256) dequant_nf4_kernel(
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const uint32_t byte = (word[u] >> (8 * b)) & 0xFFu;   // little endian: byte b
-            o[2 * b] = cvt_out<T>(lut[byte >> 4] * am[u]);
-            o[2 * b + 1] = cvt_out<T>(lut[byte & 0xFu] * am[u]);
+            o[2 * b] = cvt_out<T>(lut[(byte >> 4) * 32] * am[u]);
+            o[2 * b + 1] = cvt_out<T>(lut[(byte & 0xFu) * 32] * am[u]);
           }
           int4* dst = reinterpret_cast<int4*>(out + w * 8);
 #pragma unroll
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(256) dequant_nf4_kernel(
     const float am = absmax_of(e);
     const uint8_t byte = packed[e >> 1];
     const int q = (e & 1) ? (byte & 0xF) : (byte >> 4);
-    out[e] = cvt_out<T>(lut[q] * am);
+    out[e] = cvt_out<T>(lut[q * 32] * am);
   }
 }
 

@@ -134,26 +134,25 @@ __global__ void __launch_bounds__(256) rms_bwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-per-row variants (rows of up to 32*NV 16-byte vectors, e.g. H <= 4096 in bf16).  Each lane
-// keeps its NV raw vectors of the row in registers: NV independent 16-byte loads are in flight
-// per lane (a full row = NV coalesced 512-byte warp requests), the reduction is five shuffles
-// and there is no block barrier, so a SM holds a dozen rows in flight instead of four.
+// Two-warps-per-row variants (64-thread CTA = one row at a time, rows of up to 64*NV 16-byte
+// vectors, i.e. H <= 4096 in bf16).  Each thread keeps its NV raw vectors of the row in registers:
+// NV independent 16-byte loads are in flight per thread (a full row = NV coalesced 1-KB
+// requests) and small CTAs let a SM hold 8-16 rows in flight instead of four.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NV, bool GEMMA>
-__global__ void __launch_bounds__(128) rms_fwd_warp_kernel(
+__global__ void __launch_bounds__(64) rms_fwd_warp_kernel(
     const T* __restrict__ X, int64_t xs, const void* __restrict__ W, int wdt,
     T* __restrict__ Y, int64_t ys, float* __restrict__ r, int64_t n_rows, int n_cols, float eps) {
   constexpr int V = DT<T>::VEC;
-  const int lane = threadIdx.x & 31;
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
   const int nvec = n_cols / V;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp; row < n_rows; row += nwarps) {
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const T* x = X + row * xs;
     Vec16<T> raw[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int v = j * 32 + lane;
+      const int v = j * 64 + tid;
       if (v < nvec) {
         int4 q = __ldcs(reinterpret_cast<const int4*>(x + (int64_t)v * V));
         raw[j] = *reinterpret_cast<Vec16<T>*>(&q);
@@ -162,23 +161,24 @@ __global__ void __launch_bounds__(128) rms_fwd_warp_kernel(
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      if (j * 32 + lane < nvec) {
+      if (j * 64 + tid < nvec) {
 #pragma unroll
         for (int i = 0; i < V; ++i) { const float f = DT<T>::to_f(raw[j].v[i]); ss += f * f; }
       }
     }
-    ss = warp_sum(ss);
+    ss = block_sum(ss, red);
     const float inv = rsqrtf(ss / (float)n_cols + eps);
-    if (lane == 0) r[row] = inv;
+    if (tid == 0) r[row] = inv;
     T* y = Y + row * ys;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int v = j * 32 + lane;
+      const int v = j * 64 + tid;
       if (v < nvec) {
-        float o[V];
+        float o[V], wrow[V];
+        load_vec_as_f<V>(W, wdt, (int64_t)v * V, wrow);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float wv = load_as_f(W, wdt, v * V + i);
+          float wv = wrow[i];
           if (GEMMA) wv += 1.0f;
           float normed = DT<T>::to_f(raw[j].v[i]) * inv;
           if (!GEMMA) normed = round_to(wdt, normed);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128) rms_fwd_warp_kernel(
 // backward: TWO warps per row (one 64-thread CTA = one row at a time) so that the two raw
 // operand rows (dY and X) cost 2*NV vectors per lane with NV <= 8 -- no spills at H = 4096.
 template <typename T, int NV, bool GEMMA>
-__global__ void __launch_bounds__(64) rms_bwd_warp_kernel(
+__global__ void __launch_bounds__(64, 6) rms_bwd_warp_kernel(
     const T* dY, int64_t dys, const T* __restrict__ X, int64_t xs, const void* __restrict__ W,
     int wdt, const float* __restrict__ r, T* dX, int64_t dxs, int64_t n_rows, int n_cols) {
   constexpr int V = DT<T>::VEC;
@@ -223,9 +223,11 @@ __global__ void __launch_bounds__(64) rms_bwd_warp_kernel(
     for (int j = 0; j < NV; ++j) {
       const int v = j * 64 + tid;
       if (v < nvec) {
+        float wrow[V];
+        load_vec_as_f<V>(W, wdt, (int64_t)v * V, wrow);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float wv = load_as_f(W, wdt, v * V + i);
+          float wv = wrow[i];
           if (GEMMA) wv += 1.0f;
           acc += (DT<T>::to_f(rdy[j].v[i]) * wv) * (DT<T>::to_f(rx[j].v[i]) * inv);
         }
@@ -238,10 +240,11 @@ __global__ void __launch_bounds__(64) rms_bwd_warp_kernel(
     for (int j = 0; j < NV; ++j) {
       const int v = j * 64 + tid;
       if (v < nvec) {
-        float o[V];
+        float o[V], wrow[V];
+        load_vec_as_f<V>(W, wdt, (int64_t)v * V, wrow);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float wv = load_as_f(W, wdt, v * V + i);
+          float wv = wrow[i];
           if (GEMMA) wv += 1.0f;
           const float dyw = DT<T>::to_f(rdy[j].v[i]) * wv;
           const float nrm = DT<T>::to_f(rx[j].v[i]) * inv;
@@ -282,13 +285,15 @@ template <typename T, bool GEMMA>
 static int rms_fwd_t(const void* X, int64_t xs, const void* W, int wdt, void* Y, int64_t ys,
                      float* r, int64_t n_rows, int n_cols, float eps, cudaStream_t st) {
   const int nvec = n_cols / DT<T>::VEC;
-  if (nvec <= 32 * 16 && n_rows >= 64) {
+  if (nvec <= 64 * 8 && n_rows >= 64) {
+    const int64_t cap = (int64_t)UB_SM_COUNT * 16;
+    const int grid = (int)(n_rows < cap ? n_rows : cap);
 #define RW(NV)                                                                                   \
-  rms_fwd_warp_kernel<T, NV, GEMMA><<<warp_grid(n_rows, 16), 128, 0, st>>>(                       \
+  rms_fwd_warp_kernel<T, NV, GEMMA><<<grid, 64, 0, st>>>(                                         \
       (const T*)X, xs, W, wdt, (T*)Y, ys, r, n_rows, n_cols, eps)
-    if (nvec <= 32 * 4) RW(4);
-    else if (nvec <= 32 * 8) RW(8);
-    else RW(16);
+    if (nvec <= 64 * 2) RW(2);
+    else if (nvec <= 64 * 4) RW(4);
+    else RW(8);
 #undef RW
     return UB200_OK;
   }

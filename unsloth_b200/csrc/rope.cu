@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(512) rope_kernel(
     const int s = (int)(row - (int64_t)b * seqlen);
     const int pos = indices ? indices[row] : s;
     float c[V], sn[V];
+    load_vec_as_f<V>(cos, table_dt, (int64_t)pos * cos_rs + d0, c);
+    load_vec_as_f<V>(sin, table_dt, (int64_t)pos * sin_rs + d0, sn);
+    if (backward) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      c[i] = load_as_f(cos, table_dt, (int64_t)pos * cos_rs + d0 + i);
-      const float sv = load_as_f(sin, table_dt, (int64_t)pos * sin_rs + d0 + i);
-      sn[i] = backward ? -sv : sv;
+      for (int i = 0; i < V; ++i) sn[i] = -sn[i];
     }
     if (head_in_pass >= heads_per_pass) continue;
     for (int h0 = head_in_pass; h0 < total_heads; h0 += HP * heads_per_pass) {
