@@ -31,73 +31,48 @@ template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v;
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
 
-// Warp-coalesced expansion: per iteration a warp expands 128 contiguous packed bytes (one
-// 32-bit word per lane, a fully coalesced 128-byte load) into 256 weights and stores them as
-// one contiguous 512-byte (bf16/fp16) or 1-KB (fp32) run, 16 bytes per lane per store.  Four
-// iterations are in flight per thread.  absmax is either a ready fp32 array (absmax_f32 != null:
-// bitsandbytes-compatible stage 2) or rebuilt on the fly from the double-quantised statistics.
+// Each thread expands 16 packed bytes (32 weights, half a 64-block).  absmax is either a
+// ready fp32 array (absmax_f32 != null: bitsandbytes-compatible stage 2) or rebuilt on the fly
+// from the double-quantised statistics.
 template <typename T>
 __global__ void __launch_bounds__(256) dequant_nf4_kernel(
     const uint8_t* __restrict__ packed, const float* __restrict__ absmax_f32,
     const uint8_t* __restrict__ absmax_q, const float* __restrict__ code2,
     const float* __restrict__ absmax2, const float* __restrict__ offset, T* __restrict__ out,
     int64_t n, int blocksize, int blocksize2) {
-  // one private copy of the 16-entry code book per shared-memory bank (entry q of lane l at
-  // word q*32 + l): every lookup is conflict free whatever the nibble pattern
-  __shared__ float lut_b[16 * 32];
-  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) lut_b[i] = kNF4[i >> 5];
+  __shared__ float lut[16];
+  if (threadIdx.x < 16) lut[threadIdx.x] = kNF4[threadIdx.x];
   __syncthreads();
-  const float* lut = lut_b + (threadIdx.x & 31);
   const float off = offset ? *offset : 0.f;
-  auto absmax_of = [&](int64_t e) {
-    const int64_t blk = e / blocksize;
-    return absmax_f32 ? absmax_f32[blk]
-                      : __fadd_rn(__fmul_rn(code2[absmax_q[blk]], absmax2[blk / blocksize2]), off);
-  };
-  constexpr int UNROLL = 4;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_words = n / 8;                       // full 8-weight words
-  const bool fast = (blocksize % 8) == 0;
-  if (fast) {
-    for (int64_t w0 = warp * (32 * UNROLL); w0 < n_words; w0 += nwarps * (32 * UNROLL)) {
-      uint32_t word[UNROLL];
-      float am[UNROLL];
+  const int64_t n_chunks = (n + 31) / 32;  // 32 weights per thread-chunk
+  for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunks;
+       ch += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = ch * 32;
+    if (e0 + 32 <= n && blocksize >= 32 && (blocksize % 32) == 0) {
+      const int64_t blk = e0 / blocksize;
+      const float am = absmax_f32 ? absmax_f32[blk]
+                                  : __fadd_rn(__fmul_rn(code2[absmax_q[blk]], absmax2[blk / blocksize2]), off);
+      const int4 raw = __ldcs(reinterpret_cast<const int4*>(packed + e0 / 2));
+      const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
+      alignas(16) T o[32];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t w = w0 + u * 32 + lane;
-        if (w < n_words) {
-          word[u] = __ldcs(reinterpret_cast<const uint32_t*>(packed) + w);
-          am[u] = absmax_of(w * 8);
-        }
+      for (int i = 0; i < 16; ++i) {
+        o[2 * i] = cvt_out<T>(lut[b[i] >> 4] * am);
+        o[2 * i + 1] = cvt_out<T>(lut[b[i] & 0xF] * am);
       }
+      int4* dst = reinterpret_cast<int4*>(out + e0);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t w = w0 + u * 32 + lane;
-        if (w < n_words) {
-          alignas(16) T o[8];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const uint32_t byte = (word[u] >> (8 * b)) & 0xFFu;   // little endian: byte b
-            o[2 * b] = cvt_out<T>(lut[(byte >> 4) * 32] * am[u]);
-            o[2 * b + 1] = cvt_out<T>(lut[(byte & 0xFu) * 32] * am[u]);
-          }
-          int4* dst = reinterpret_cast<int4*>(out + w * 8);
-#pragma unroll
-          for (int q = 0; q < (int)(8 * sizeof(T) / 16); ++q) dst[q] = reinterpret_cast<int4*>(o)[q];
-        }
+      for (int i = 0; i < (int)(32 * sizeof(T) / 16); ++i) dst[i] = reinterpret_cast<int4*>(o)[i];
+    } else {
+      for (int64_t e = e0; e < n && e < e0 + 32; ++e) {
+        const int64_t blk = e / blocksize;
+        const float am = absmax_f32 ? absmax_f32[blk]
+                                    : __fadd_rn(__fmul_rn(code2[absmax_q[blk]], absmax2[blk / blocksize2]), off);
+        const uint8_t byte = packed[e >> 1];
+        const int q = (e & 1) ? (byte & 0xF) : (byte >> 4);
+        out[e] = cvt_out<T>(lut[q] * am);
       }
     }
-  }
-  // tail (and the generic path for block sizes that are not a multiple of 8)
-  const int64_t e_start = fast ? n_words * 8 : 0;
-  for (int64_t e = e_start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const float am = absmax_of(e);
-    const uint8_t byte = packed[e >> 1];
-    const int q = (e & 1) ? (byte & 0xF) : (byte >> 4);
-    out[e] = cvt_out<T>(lut[q * 32] * am);
   }
 }
 
@@ -156,8 +131,8 @@ template <typename T>
 static void launch_dequant(const uint8_t* packed, const float* absmax_f32, const uint8_t* absmax_q,
                            const float* code2, const float* absmax2, const float* offset, void* out,
                            int64_t n, int blocksize, int blocksize2, cudaStream_t st) {
-  const int64_t threads_needed = (n / 8 + 3) / 4;      // 4 words per thread
-  dequant_nf4_kernel<T><<<grid_for(threads_needed, 256, 8), 256, 0, st>>>(
+  const int64_t chunks = (n + 31) / 32;
+  dequant_nf4_kernel<T><<<grid_for(chunks, 256, 16), 256, 0, st>>>(
       packed, absmax_f32, absmax_q, code2, absmax2, offset, (T*)out, n, blocksize, blocksize2);
 }
 

@@ -133,135 +133,6 @@ __global__ void __launch_bounds__(256) rms_bwd_kernel(
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Two-warps-per-row variants (64-thread CTA = one row at a time, rows of up to 64*NV 16-byte
-// vectors, i.e. H <= 4096 in bf16).  Each thread keeps its NV raw vectors of the row in registers:
-// NV independent 16-byte loads are in flight per thread (a full row = NV coalesced 1-KB
-// requests) and small CTAs let a SM hold 8-16 rows in flight instead of four.
-// ---------------------------------------------------------------------------------------------
-template <typename T, int NV, bool GEMMA>
-__global__ void __launch_bounds__(64) rms_fwd_warp_kernel(
-    const T* __restrict__ X, int64_t xs, const void* __restrict__ W, int wdt,
-    T* __restrict__ Y, int64_t ys, float* __restrict__ r, int64_t n_rows, int n_cols, float eps) {
-  constexpr int V = DT<T>::VEC;
-  __shared__ float red[32];
-  const int tid = threadIdx.x;
-  const int nvec = n_cols / V;
-  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const T* x = X + row * xs;
-    Vec16<T> raw[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = j * 64 + tid;
-      if (v < nvec) {
-        int4 q = __ldcs(reinterpret_cast<const int4*>(x + (int64_t)v * V));
-        raw[j] = *reinterpret_cast<Vec16<T>*>(&q);
-      }
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      if (j * 64 + tid < nvec) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) { const float f = DT<T>::to_f(raw[j].v[i]); ss += f * f; }
-      }
-    }
-    ss = block_sum(ss, red);
-    const float inv = rsqrtf(ss / (float)n_cols + eps);
-    if (tid == 0) r[row] = inv;
-    T* y = Y + row * ys;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = j * 64 + tid;
-      if (v < nvec) {
-        float o[V], wrow[V];
-        load_vec_as_f<V>(W, wdt, (int64_t)v * V, wrow);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          float wv = wrow[i];
-          if (GEMMA) wv += 1.0f;
-          float normed = DT<T>::to_f(raw[j].v[i]) * inv;
-          if (!GEMMA) normed = round_to(wdt, normed);
-          float prod = normed * wv;
-          if (!GEMMA) prod = round_to(wdt, prod);
-          o[i] = prod;
-        }
-        store_vec<T>(y + (int64_t)v * V, o);
-      }
-    }
-  }
-}
-
-// backward: TWO warps per row (one 64-thread CTA = one row at a time) so that the two raw
-// operand rows (dY and X) cost 2*NV vectors per lane with NV <= 8 -- no spills at H = 4096.
-template <typename T, int NV, bool GEMMA>
-__global__ void __launch_bounds__(64, 6) rms_bwd_warp_kernel(
-    const T* dY, int64_t dys, const T* __restrict__ X, int64_t xs, const void* __restrict__ W,
-    int wdt, const float* __restrict__ r, T* dX, int64_t dxs, int64_t n_rows, int n_cols) {
-  constexpr int V = DT<T>::VEC;
-  __shared__ float red[32];
-  const int tid = threadIdx.x;
-  const int nvec = n_cols / V;
-  const float n = (float)n_cols;
-  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const T* dy = dY + row * dys;
-    const T* x = X + row * xs;
-    Vec16<T> rdy[NV], rx[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = j * 64 + tid;
-      if (v < nvec) {
-        int4 a = __ldcs(reinterpret_cast<const int4*>(dy + (int64_t)v * V));
-        int4 b = __ldcs(reinterpret_cast<const int4*>(x + (int64_t)v * V));
-        rdy[j] = *reinterpret_cast<Vec16<T>*>(&a);
-        rx[j] = *reinterpret_cast<Vec16<T>*>(&b);
-      }
-    }
-    const float inv = r[row];
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = j * 64 + tid;
-      if (v < nvec) {
-        float wrow[V];
-        load_vec_as_f<V>(W, wdt, (int64_t)v * V, wrow);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          float wv = wrow[i];
-          if (GEMMA) wv += 1.0f;
-          acc += (DT<T>::to_f(rdy[j].v[i]) * wv) * (DT<T>::to_f(rx[j].v[i]) * inv);
-        }
-      }
-    }
-    acc = block_sum(acc, red);
-    const float k = inv / n;
-    T* dx = dX + row * dxs;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int v = j * 64 + tid;
-      if (v < nvec) {
-        float o[V], wrow[V];
-        load_vec_as_f<V>(W, wdt, (int64_t)v * V, wrow);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          float wv = wrow[i];
-          if (GEMMA) wv += 1.0f;
-          const float dyw = DT<T>::to_f(rdy[j].v[i]) * wv;
-          const float nrm = DT<T>::to_f(rx[j].v[i]) * inv;
-          o[i] = k * (n * dyw - nrm * acc);
-        }
-        store_vec<T>(dx + (int64_t)v * V, o);
-      }
-    }
-  }
-}
-
-static inline int warp_grid(int64_t n_rows, int warps_per_sm) {
-  int64_t ctas = ((int64_t)UB_SM_COUNT * warps_per_sm + 3) / 4;       // 4 warps per CTA
-  int64_t need = (n_rows + 3) / 4;
-  return (int)(need < ctas ? need : ctas);
-}
-
 template <typename T, bool GEMMA, typename F>
 static int dispatch_vpt(int n_cols, F&& launch) {
   constexpr int V = DT<T>::VEC;
@@ -284,19 +155,6 @@ static inline int rows_grid(int64_t n_rows) {
 template <typename T, bool GEMMA>
 static int rms_fwd_t(const void* X, int64_t xs, const void* W, int wdt, void* Y, int64_t ys,
                      float* r, int64_t n_rows, int n_cols, float eps, cudaStream_t st) {
-  const int nvec = n_cols / DT<T>::VEC;
-  if (nvec <= 64 * 8 && n_rows >= 64) {
-    const int64_t cap = (int64_t)UB_SM_COUNT * 16;
-    const int grid = (int)(n_rows < cap ? n_rows : cap);
-#define RW(NV)                                                                                   \
-  rms_fwd_warp_kernel<T, NV, GEMMA><<<grid, 64, 0, st>>>(                                         \
-      (const T*)X, xs, W, wdt, (T*)Y, ys, r, n_rows, n_cols, eps)
-    if (nvec <= 64 * 2) RW(2);
-    else if (nvec <= 64 * 4) RW(4);
-    else RW(8);
-#undef RW
-    return UB200_OK;
-  }
   return dispatch_vpt<T, GEMMA>(n_cols, [&](auto vpt, int threads) {
     rms_fwd_kernel<T, decltype(vpt)::value, GEMMA><<<rows_grid(n_rows), threads, 0, st>>>(
         (const T*)X, xs, W, wdt, (T*)Y, ys, r, n_rows, n_cols, eps);
@@ -307,19 +165,6 @@ template <typename T, bool GEMMA>
 static int rms_bwd_t(const void* dY, int64_t dys, const void* X, int64_t xs, const void* W,
                      int wdt, const float* r, void* dX, int64_t dxs, int64_t n_rows, int n_cols,
                      cudaStream_t st) {
-  const int nvec = n_cols / DT<T>::VEC;
-  if (nvec <= 64 * 8 && n_rows >= 64) {
-    const int64_t cap = (int64_t)UB_SM_COUNT * 10;
-    const int grid = (int)(n_rows < cap ? n_rows : cap);
-#define RW(NV)                                                                                   \
-  rms_bwd_warp_kernel<T, NV, GEMMA><<<grid, 64, 0, st>>>(                                         \
-      (const T*)dY, dys, (const T*)X, xs, W, wdt, r, (T*)dX, dxs, n_rows, n_cols)
-    if (nvec <= 64 * 2) RW(2);
-    else if (nvec <= 64 * 4) RW(4);
-    else RW(8);
-#undef RW
-    return UB200_OK;
-  }
   return dispatch_vpt<T, GEMMA>(n_cols, [&](auto vpt, int threads) {
     rms_bwd_kernel<T, decltype(vpt)::value, GEMMA><<<rows_grid(n_rows), threads, 0, st>>>(
         (const T*)dY, dys, (const T*)X, xs, W, wdt, r, (T*)dX, dxs, n_rows, n_cols);

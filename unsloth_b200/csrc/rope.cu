@@ -22,9 +22,7 @@
 
 namespace ub {
 
-// One CTA iteration = one token row; every thread rotates HP heads of that row with the SAME
-// cos/sin registers, keeping 2*HP independent 16-byte loads in flight.
-template <typename T, int HP>
+template <typename T>
 __global__ void __launch_bounds__(512) rope_kernel(
     T* Q, int64_t q_bs, int64_t q_hs, int64_t q_ss, T* K, int64_t k_bs, int64_t k_hs,
     int64_t k_ss, const void* __restrict__ cos, int64_t cos_rs, const void* __restrict__ sin,
@@ -44,47 +42,33 @@ __global__ void __launch_bounds__(512) rope_kernel(
     const int s = (int)(row - (int64_t)b * seqlen);
     const int pos = indices ? indices[row] : s;
     float c[V], sn[V];
-    load_vec_as_f<V>(cos, table_dt, (int64_t)pos * cos_rs + d0, c);
-    load_vec_as_f<V>(sin, table_dt, (int64_t)pos * sin_rs + d0, sn);
-    if (backward) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) sn[i] = -sn[i];
+    for (int i = 0; i < V; ++i) {
+      c[i] = load_as_f(cos, table_dt, (int64_t)pos * cos_rs + d0 + i);
+      float sv = load_as_f(sin, table_dt, (int64_t)pos * sin_rs + d0 + i);
+      sn[i] = backward ? -sv : sv;
     }
     if (head_in_pass >= heads_per_pass) continue;
-    for (int h0 = head_in_pass; h0 < total_heads; h0 += HP * heads_per_pass) {
-      T* p[HP];
-      Vec16<T> r1[HP], r2[HP];
+    for (int h = head_in_pass; h < total_heads; h += heads_per_pass) {
+      T* p = (h < n_heads_q)
+                 ? Q + (int64_t)b * q_bs + (int64_t)h * q_hs + (int64_t)s * q_ss
+                 : K + (int64_t)b * k_bs + (int64_t)(h - n_heads_q) * k_hs + (int64_t)s * k_ss;
+      float x1[V], x2[V], o1[V], o2[V];
+      load_vec<T>(p + d0, x1);
+      load_vec<T>(p + half + d0, x2);
 #pragma unroll
-      for (int u = 0; u < HP; ++u) {
-        const int h = h0 + u * heads_per_pass;
-        p[u] = nullptr;
-        if (h < total_heads) {
-          p[u] = (h < n_heads_q)
-                     ? Q + (int64_t)b * q_bs + (int64_t)h * q_hs + (int64_t)s * q_ss
-                     : K + (int64_t)b * k_bs + (int64_t)(h - n_heads_q) * k_hs + (int64_t)s * k_ss;
-          r1[u] = *reinterpret_cast<const Vec16<T>*>(p[u] + d0);
-          r2[u] = *reinterpret_cast<const Vec16<T>*>(p[u] + half + d0);
-        }
+      for (int i = 0; i < V; ++i) {
+        const float a1 = round_to(comp_dt, x1[i]), a2 = round_to(comp_dt, x2[i]);
+        // q1*cos - q2*sin ; q2*cos + q1*sin, each op rounded to the compute dtype
+        const float m11 = round_to(comp_dt, __fmul_rn(a1, c[i]));
+        const float m22 = round_to(comp_dt, __fmul_rn(a2, sn[i]));
+        const float m21 = round_to(comp_dt, __fmul_rn(a2, c[i]));
+        const float m12 = round_to(comp_dt, __fmul_rn(a1, sn[i]));
+        o1[i] = round_to(comp_dt, __fsub_rn(m11, m22));
+        o2[i] = round_to(comp_dt, __fadd_rn(m21, m12));
       }
-#pragma unroll
-      for (int u = 0; u < HP; ++u) {
-        if (p[u] == nullptr) continue;
-        float o1[V], o2[V];
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float a1 = round_to(comp_dt, DT<T>::to_f(r1[u].v[i]));
-          const float a2 = round_to(comp_dt, DT<T>::to_f(r2[u].v[i]));
-          // q1*cos - q2*sin ; q2*cos + q1*sin, each op rounded to the compute dtype
-          const float m11 = round_to(comp_dt, __fmul_rn(a1, c[i]));
-          const float m22 = round_to(comp_dt, __fmul_rn(a2, sn[i]));
-          const float m21 = round_to(comp_dt, __fmul_rn(a2, c[i]));
-          const float m12 = round_to(comp_dt, __fmul_rn(a1, sn[i]));
-          o1[i] = round_to(comp_dt, __fsub_rn(m11, m22));
-          o2[i] = round_to(comp_dt, __fadd_rn(m21, m12));
-        }
-        store_vec<T>(p[u] + d0, o1);
-        store_vec<T>(p[u] + half + d0, o2);
-      }
+      store_vec<T>(p + d0, o1);
+      store_vec<T>(p + half + d0, o2);
     }
   }
 }
@@ -110,17 +94,16 @@ extern "C" int ub200_rope_qk(void* Q, int64_t q_batch_stride, int64_t q_head_str
     return UB200_ERR_BAD_ARG;
   const int vec_per_half = half / V;
   if (vec_per_half > 512) return UB200_ERR_UNSUPPORTED;
-  // HP heads per thread: one pass over all heads when ceil(heads/HP) * vec_per_half <= 512
-  constexpr int HP = 2;
+  // one pass over all heads if it fits in 256 threads
   int heads = n_heads_q + n_heads_k;
-  int threads = vec_per_half * ((heads + HP - 1) / HP);
+  int threads = vec_per_half * heads;
   if (threads > 512) threads = (512 / vec_per_half) * vec_per_half;
   threads = ((threads + 31) / 32) * 32;
   if (threads > 512) threads = 512;
-  int64_t g = (int64_t)UB_SM_COUNT * 16;
+  int64_t g = (int64_t)UB_SM_COUNT * 8;
   const int grid = (int)(n_rows < g ? n_rows : g);
 #define GO(T)                                                                                  \
-  rope_kernel<T, HP><<<grid, threads, 0, stream>>>(                                            \
+  rope_kernel<T><<<grid, threads, 0, stream>>>(                                                \
       (T*)Q, q_batch_stride, q_head_stride, q_seq_stride, (T*)K, k_batch_stride, k_head_stride, \
       k_seq_stride, cos, cos_row_stride, sin, sin_row_stride, indices, seqlen, n_heads_q,       \
       n_heads_k, head_dim, backward, table_dtype, compute_dtype, n_rows)
