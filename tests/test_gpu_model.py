@@ -1,0 +1,140 @@
+"""End-to-end parity of the patched model forward+backward (unsloth_b200.patch.install) against the
+REFERENCE CPU PATH of BASELINE.json configs[0]: the stock HuggingFace implementation in torch eager
+fp32 on the CPU with plain LoRA (y = x W^T + s (x A^T) B^T), carrying the same (dequantised) weights.
+
+Our path runs NF4 + bf16 on the GPU, so the gate is: loss within 2 % and every LoRA gradient
+pointing the same way (cosine > 0.98, norm ratio within 15 %)."""
+import copy
+import math
+
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TINY = dict(hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2,
+            head_dim=64, vocab_size=1024)
+
+
+class PlainLoRA(nn.Module):
+    def __init__(self, W, A, B, s):
+        super().__init__()
+        self.W = nn.Parameter(W, requires_grad=False)
+        self.A, self.B, self.s = nn.Parameter(A), nn.Parameter(B), s
+
+    def forward(self, x):
+        return x @ self.W.t() + self.s * (x @ self.A.t()) @ self.B.t()
+
+
+def _reference_from(model, cfg):
+    """Stock HF model (eager, fp32, CPU) with the dequantised weights + LoRA of `model`."""
+    from transformers import AutoModelForCausalLM
+    from unsloth_b200.kernels import fast_dequantize, get_lora_parameters
+    cfg = copy.deepcopy(cfg)
+    cfg._attn_implementation = "eager"
+    ref = AutoModelForCausalLM.from_config(cfg).float()
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()
+          if "lora_" not in k and "base_layer" not in k}
+    missing = ref.load_state_dict(sd, strict=False)
+    for lo, lr in zip(model.model.layers, ref.model.layers):
+        for po, pr in ((lo.self_attn, lr.self_attn), (lo.mlp, lr.mlp)):
+            for name in ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"):
+                if not hasattr(po, name):
+                    continue
+                W, Wq, A, B, s = get_lora_parameters(getattr(po, name))
+                Wd = fast_dequantize(W, Wq).float().cpu()
+                setattr(pr, name, PlainLoRA(Wd, A.detach().float().cpu().clone(), B.detach().float().cpu().clone(), s))
+    for p_ in ref.parameters():
+        p_.requires_grad_(False)
+    for m in ref.modules():
+        if isinstance(m, PlainLoRA):
+            m.A.requires_grad_(True); m.B.requires_grad_(True)
+    return ref
+
+
+@pytest.mark.parametrize("name,extra,seq", [
+    ("llama-3-8b", {}, 96),
+    ("llama-3.2-1b", {}, 128),                       # configs[0] architecture (llama3 rope scaling, tied embeddings)
+    ("mistral-7b-v0.3", {}, 80),
+    ("gemma-2-9b", {"query_pre_attn_scalar": 64}, 72),
+])
+def test_patched_model_matches_reference_cpu_path(name, extra, seq):
+    from unsloth_b200.patch import build_qlora_model, hf_config
+    from unsloth_b200.kernels import get_lora_parameters
+    kw = dict(TINY, **extra)
+    model = build_qlora_model(name, r=8, lora_alpha=16, device=DEV, num_hidden_layers=2, init_b_std=0.05, **kw)
+    cfg = hf_config(name, 2, **kw)
+    ref = _reference_from(model, cfg)
+    torch.manual_seed(1)
+    ids = torch.randint(0, kw["vocab_size"], (2, seq))
+    labels = ids.clone(); labels[0, :5] = -100
+    out = model(input_ids=ids.to(DEV), labels=labels.to(DEV))
+    out.loss.backward()
+    ref_out = ref(input_ids=ids, labels=labels)
+    ref_out.loss.backward()
+    assert math.isfinite(out.loss.item())
+    assert abs(out.loss.item() - ref_out.loss.item()) <= 0.02 * abs(ref_out.loss.item()), (out.loss.item(), ref_out.loss.item())
+    worst = 1.0
+    for lo, lr in zip(model.model.layers, ref.model.layers):
+        for po, pr in ((lo.self_attn, lr.self_attn), (lo.mlp, lr.mlp)):
+            for pn in ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"):
+                if not hasattr(po, pn):
+                    continue
+                _, _, A, B, _ = get_lora_parameters(getattr(po, pn))
+                for ours, theirs in ((A.grad, getattr(pr, pn).A.grad), (B.grad, getattr(pr, pn).B.grad)):
+                    a, b = ours.float().cpu().flatten(), theirs.flatten()
+                    cos = torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)
+                    worst = min(worst, cos.item())
+                    assert cos > 0.98, (name, pn, cos.item())
+                    assert 0.85 < (a.norm() / (b.norm() + 1e-30)).item() < 1.15, (name, pn)
+    assert worst > 0.98
+
+
+def test_sliding_window_and_softcap_route():
+    """Mistral / Gemma-2 deltas go through flash-attn with the reference's arguments
+    (mistral.py:112-128, gemma2.py:159): check against an explicit masked softmax."""
+    from unsloth_b200.patch import _attention
+    torch.manual_seed(0)
+    B, S, H, D, sw, cap = 1, 64, 2, 64, 16, 20.0
+    q, k, v = (torch.randn(B, S, H, D, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    out = _attention(q, k, v, D ** -0.5, (sw, sw), cap)
+    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float()) * D ** -0.5
+    s = cap * torch.tanh(s / cap)
+    i = torch.arange(S, device=DEV)[:, None]; j = torch.arange(S, device=DEV)[None, :]
+    mask = (j <= i) & (j >= i - sw)
+    s = s.masked_fill(~mask, float("-inf"))
+    ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v.float())
+    assert (out.float() - ref).abs().max() < 3e-2
+    # plain causal route (cuDNN SDPA when available) against the same formula
+    out2 = _attention(q, k, v, D ** -0.5, (-1, -1), 0.0)
+    s2 = (torch.einsum("bihd,bjhd->bhij", q.float(), k.float()) * D ** -0.5).masked_fill(~(j <= i), float("-inf"))
+    ref2 = torch.einsum("bhij,bjhd->bihd", torch.softmax(s2, -1), v.float())
+    assert (out2.float() - ref2).abs().max() < 3e-2
+
+
+def test_training_reduces_loss_and_is_deterministic():
+    """Behavioural smoke like the reference's T4 CI (tests/kaggle/t4_smoke): loss goes down on a
+    repeated batch and two fresh runs reproduce the loss trace."""
+    from unsloth_b200.ddp import FlatLoRABucket
+    from unsloth_b200.patch import build_qlora_model, lora_parameters
+
+    def run():
+        model = build_qlora_model("llama-3-8b", r=8, lora_alpha=16, device=DEV, num_hidden_layers=2, **TINY)
+        bucket = FlatLoRABucket(lora_parameters(model), lr=2e-3, weight_decay=0.0)
+        g = torch.Generator().manual_seed(7)
+        ids = torch.randint(0, TINY["vocab_size"], (2, 64), generator=g).to(DEV)
+        losses = []
+        for _ in range(8):
+            bucket.zero_grad()
+            loss = model(input_ids=ids, labels=ids).loss
+            loss.backward()
+            bucket.step()
+            losses.append(loss.item())
+        return losses
+    a, b = run(), run()
+    assert a[-1] < a[0] - 0.05, a
+    # our kernels are deterministic (fixed-order split-K, no atomics); the attention library's
+    # backward may not be, so allow last-bit noise there
+    assert max(abs(x - y) for x, y in zip(a, b)) < 2e-3, (a, b)

@@ -59,6 +59,8 @@ struct Params {
   int accumulate;        // C = alpha*acc + C
   float alpha;
   int ab_fp16;           // operands are fp16 instead of bf16
+  int raster_mode;       // 0: groups of `raster_group` M-tiles stay L2-resident, sweep N; 1: N-groups, sweep M
+  int raster_group;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -247,6 +249,32 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn,
   return d;
 }
 
+// L2-aware rasterisation of the tile grid.  The two 63 MB L2 halves each keep their own copy of
+// data shared across dies, so the operand that is re-used across a sweep must fit in ~30 MB:
+//   mode 0: `group` M-tiles stay resident while all N-tiles stream past (m fastest inside a group,
+//           so the CTAs running together share the same weight tile);
+//   mode 1: `group` N-tiles stay resident while all M-tiles stream past.
+__device__ __forceinline__ void raster_coords(int tile, int m_total, int n_total, int mode, int group,
+                                              int& m_idx, int& n_idx) {
+  if (mode == 0) {
+    const int per = group * n_total;
+    const int g = tile / per;
+    const int rem = tile - g * per;
+    const int left = m_total - g * group;
+    const int ge = left < group ? left : group;
+    n_idx = rem / ge;
+    m_idx = g * group + (rem - n_idx * ge);
+  } else {
+    const int per = group * m_total;
+    const int g = tile / per;
+    const int rem = tile - g * per;
+    const int left = n_total - g * group;
+    const int ge = left < group ? left : group;
+    m_idx = rem / ge;
+    n_idx = g * group + (rem - m_idx * ge);
+  }
+}
+
 // Epilogue store of 32 consecutive accumulator columns of one row: alpha, optional beta=1
 // read-modify-write, conversion to the output dtype, 16-byte global stores.
 __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&r)[32], bool has_k,
@@ -377,9 +405,7 @@ gemm_kernel(const __grid_constant__ Params p) {
     kb1 = min(total_kb, kb0 + per);
   };
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
-    // m fastest: the CTAs running concurrently share the same B (weight) tiles in L2
-    m_blk = tile % p.m_tiles;
-    n_blk = tile / p.m_tiles;
+    raster_coords(tile, p.m_tiles, p.n_tiles, p.raster_mode, p.raster_group, m_blk, n_blk);
   };
 
   if (warp == 0) {
@@ -571,8 +597,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
     kb1 = min(total_kb, kb0 + per);
   };
   auto tile_coords = [&](int tile, int& m_pair, int& n_blk) {
-    m_pair = tile % m_pairs;
-    n_blk = tile / m_pairs;
+    raster_coords(tile, m_pairs, p.n_tiles, p.raster_mode, p.raster_group, m_pair, n_blk);
   };
 
   if (warp == 0) {
@@ -849,6 +874,21 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     p.split_stride = 0;
     p.c_dtype = c_dtype;
     p.accumulate = accumulate;
+  }
+  {
+    // choose which operand stays L2-resident (see raster_coords)
+    const int64_t k_total = (int64_t)total_kb * BLOCK_K;
+    const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
+    const int m_t = (M + tile_m - 1) / tile_m;
+    const int64_t a_tile = (int64_t)tile_m * k_total * 2, b_tile = (int64_t)bn * k_total * 2;
+    const int64_t a_total = (int64_t)M * k_total * 2, b_total = (int64_t)N * k_total * 2;
+    const int64_t cap = 28ll << 20;
+    int64_t gm = cap / a_tile; if (gm < 1) gm = 1; if (gm > m_t) gm = m_t;
+    int64_t gn = cap / b_tile; if (gn < 1) gn = 1; if (gn > p.n_tiles) gn = p.n_tiles;
+    const int64_t cost_a = a_total + b_total * ((m_t + gm - 1) / gm);
+    const int64_t cost_b = b_total + a_total * ((p.n_tiles + gn - 1) / gn);
+    if (cost_a <= cost_b) { p.raster_mode = 0; p.raster_group = (int)gm; }
+    else { p.raster_mode = 1; p.raster_group = (int)gn; }
   }
   int rc;
   if (pair) {

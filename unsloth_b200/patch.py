@@ -96,9 +96,28 @@ class RotaryCache:
 # ---------------------------------------------------------------------------------------------
 # fast forwards
 # ---------------------------------------------------------------------------------------------
+_SDPA_CUDNN = {"ok": None}
+
+
 def _attention(Q, K_, V, scale, window, softcap):
-    """External library call, like the reference (attention_dispatch.py:452): causal flash-attn
-    on [B, S, H, D] views of the projection buffers (GQA native)."""
+    """External library call, like the reference's dispatcher (utils/attention_dispatch.py:298-617:
+    flash-attn | xformers | SDPA), on [B, S, H, D] views of the projection buffers (GQA native,
+    no copies).  Plain causal attention goes to torch SDPA's cuDNN backend (Blackwell-native fused
+    attention, ~3x flash-attn 2 on B200, benchmarks/attn_bench.py); sliding window / soft-capping
+    (Mistral, Gemma-2) go to flash-attn 2, which supports them."""
+    if window == (-1, -1) and not softcap and _SDPA_CUDNN["ok"] is not False:
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        try:
+            with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+                o = F.scaled_dot_product_attention(Q.transpose(1, 2), K_.transpose(1, 2), V.transpose(1, 2),
+                                                   is_causal=True, scale=scale, enable_gqa=True)
+            _SDPA_CUDNN["ok"] = True
+            return o.transpose(1, 2)
+        except RuntimeError:
+            if _SDPA_CUDNN["ok"]:
+                raise
+            _SDPA_CUDNN["ok"] = False          # backend unavailable for this shape: use flash-attn
     from flash_attn import flash_attn_func
     return flash_attn_func(Q, K_, V, dropout_p=0.0, softmax_scale=scale, causal=True,
                            window_size=window, softcap=softcap)
