@@ -163,7 +163,9 @@ def DecoderLayer_fast_forward(self, hidden_states, cos, sin, position_ids=None):
 def Model_fast_forward(self, input_ids, position_ids=None):
     """models/llama.py:866-1230: embed, (Gemma: * sqrt(H) in model dtype :961-989), layers, norm."""
     h = self.embed_tokens(input_ids)
-    if self._ub_gemma:
+    if self._ub_gemma and not hasattr(self.embed_tokens, "embed_scale"):
+        # transformers >= 4.5x wraps the Gemma embedding in a *ScaledWordEmbedding that already
+        # multiplies by sqrt(H); older versions (the reference's llama.py:961-989) scale here
         h = h * torch.tensor(math.sqrt(self.config.hidden_size), dtype=h.dtype, device=h.device)
     seq_len = input_ids.shape[1]
     need = seq_len
