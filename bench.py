@@ -49,9 +49,22 @@ def parse():
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer layers (INVALID as a bench)")
     ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--bs", type=int, default=BS)
+    ap.add_argument("--preset", default=None, choices=["cfg2", "cfg3", "cfg5"],
+                    help="BASELINE.json configs[1] (default) / [2] Mistral-7B r=32 seq4096 bs2 sliding window / "
+                         "[4] Gemma-2-9B r=16 seq8192 bs1 -- cfg3/cfg5 are parity/coverage runs, not the headline")
+    ap.add_argument("--rank", type=int, default=RANK_R)
+    ap.add_argument("--sliding-window", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-tokens", type=int, default=512)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.preset == "cfg3":
+        a.model, a.seq, a.bs, a.rank = "mistral-7b-v0.3", 4096, 2, 32
+        a.sliding_window = a.sliding_window or 2048      # v0.3 ships sliding_window=null; exercise the band
+        a.no_cpu_baseline = True
+    elif a.preset == "cfg5":
+        a.model, a.seq, a.bs, a.rank = "gemma-2-9b", 8192, 1, 16
+        a.no_cpu_baseline = True
+    return a
 
 
 # ---------------------------------------------------------------------------------------------
@@ -208,8 +221,13 @@ def run_ours(args):
 
     rank, world, local = init_distributed()
     dev = torch.device("cuda", local)
-    model = build_qlora_model(args.model, r=RANK_R, lora_alpha=RANK_R, device=dev, seed=3407,
-                              num_hidden_layers=args.layers)
+    extra = {}
+    if args.sliding_window:
+        extra["sliding_window"] = args.sliding_window
+    if args.seq > 8192:
+        extra["max_position_embeddings"] = args.seq
+    model = build_qlora_model(args.model, r=args.rank, lora_alpha=args.rank, device=dev, seed=3407,
+                              num_hidden_layers=args.layers, **extra)
     bucket = FlatLoRABucket(lora_parameters(model), lr=2e-4, weight_decay=0.01)
     bucket.broadcast_params(0)
     V = model.config.vocab_size
@@ -312,8 +330,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "%s QLoRA NF4 r=%d bf16 seq%d bs%d/GPU (BASELINE.json configs[%d])" %
-                                   (args.model, RANK_R, args.seq, args.bs, 1 if world == 1 else 3),
+            "config": {"workload": "%s QLoRA NF4 r=%d bf16 seq%d bs%d/GPU (BASELINE.json configs[%d])%s" %
+                                   (args.model, args.rank, args.seq, args.bs,
+                                    {"cfg3": 2, "cfg5": 4}.get(args.preset, 1 if world == 1 else 3),
+                                    (" sliding_window=%d" % args.sliding_window) if args.sliding_window else ""),
                        "global_batch": args.bs * world, "seq_len": args.seq, "parallelism": "dp%d" % world,
                        "layers": model.config.num_hidden_layers, "gradient_checkpointing": False,
                        "optimizer": "AdamW on the flat LoRA bucket (%d params)" % bucket.numel(),

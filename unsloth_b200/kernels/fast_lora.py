@@ -129,8 +129,8 @@ class _Group:
             outs.append(Y)
         return outs, XA
 
-    def backward(self, dYs, XA, dX_out=None):
-        """dYs: list of [T, out_i].  Returns (dX [T,in], [(dA_i, dB_i) or (None, None)])."""
+    def backward(self, dYs, XA, dX_out=None, need_dX=True):
+        """dYs: list of [T, out_i].  Returns (dX [T,in] or None, [(dA_i, dB_i) or (None, None)])."""
         X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
         grads = []
         G = None
@@ -162,6 +162,8 @@ class _Group:
                 grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
         else:
             grads = [(None, None)] * len(self.projs)
+        if not need_dX:
+            return None, grads
         # dX = sum_i dY_i @ W_i  +  G @ A_cat      (one launch; W_i as MN-major operands)
         segs = []
         for slot, (dY, (W, Wq, A, B, s)) in enumerate(zip(dYs, self.projs)):
@@ -320,10 +322,11 @@ class LoRA_QKV(torch.autograd.Function):
         X2, XA = ctx.saved_tensors
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
                           (VW, VW_quant, VA, VB, VS)])
+        need_dX = ctx.needs_input_grad[0]     # False for the first layer (embedding output)
         dX, ((dQA, dQB), (dKA, dKB), (dVA, dVB)) = grp.backward(
-            [_as2d(dQ), _as2d(dK), _as2d(dV)], XA, dX_out=X2 if ctx.inplace else None)
-        return (dX.view(ctx.shape), None, None, dQA, dQB, None, None, None, dKA, dKB, None, None,
-                None, dVA, dVB, None, None)
+            [_as2d(dQ), _as2d(dK), _as2d(dV)], XA, dX_out=X2 if ctx.inplace else None, need_dX=need_dX)
+        return (dX.view(ctx.shape) if need_dX else None, None, None, dQA, dQB, None, None, None, dKA, dKB,
+                None, None, None, dVA, dVB, None, None)
 
 
 def apply_lora_qkv(self, X, inplace=True):
