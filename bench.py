@@ -54,6 +54,7 @@ def parse():
                          "[4] Gemma-2-9B r=16 seq8192 bs1 -- cfg3/cfg5 are parity/coverage runs, not the headline")
     ap.add_argument("--rank", type=int, default=RANK_R)
     ap.add_argument("--sliding-window", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-tokens", type=int, default=512)
     a = ap.parse_args()
@@ -239,7 +240,7 @@ def run_ours(args):
     host_lab = host_lab.pin_memory()
     dev_ids, dev_lab = host_ids.to(dev), host_lab.to(dev)
 
-    def train_step(ids, lab):
+    def eager_step(ids, lab):
         bucket.zero_grad()
         out = model(input_ids=ids, labels=lab)
         out.loss.backward()
@@ -247,31 +248,48 @@ def run_ours(args):
         bucket.step()
         return out.loss
 
+    graphed, graph_note = None, "disabled (--no-graph)"
+    if not args.no_graph:
+        try:
+            from unsloth_b200.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(model, bucket, args.bs, args.seq, dev)
+            graph_note = "fwd+bwd replayed from one CUDA graph (%d launches captured); all-reduce + AdamW outside" % graphed.launches_per_replay
+        except Exception as ex:  # pragma: no cover - report and fall back to eager launches
+            graphed, graph_note = None, "capture failed, eager launches: %r" % (ex,)
+            torch.cuda.synchronize()
+
+    def train_step(ids, lab):
+        return graphed.step(ids, lab) if graphed is not None else eager_step(ids, lab)
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def timed(leg):
+        step_fn = eager_step if leg == "profile" else train_step
         for i in range(args.warmup):
             if leg == "e2e":
-                ids = host_ids[i].to(dev, non_blocking=True); lab = host_lab[i].to(dev, non_blocking=True)
-                train_step(ids, lab).item()
+                step_fn(host_ids[i], host_lab[i]).item() if graphed is not None else \
+                    step_fn(host_ids[i].to(dev, non_blocking=True), host_lab[i].to(dev, non_blocking=True)).item()
             else:
-                train_step(dev_ids[i], dev_lab[i])
+                step_fn(dev_ids[i], dev_lab[i])
         barrier()
         L.launch_count = 0
-        KU.GEMM_EVENTS = [] if leg == "resident" else None
+        KU.GEMM_EVENTS = [] if leg == "profile" else None
         torch.cuda.reset_peak_memory_stats()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         loss = None
         for i in range(args.warmup, total_steps):
             if leg == "e2e":
-                ids = host_ids[i].to(dev, non_blocking=True); lab = host_lab[i].to(dev, non_blocking=True)
-                loss = train_step(ids, lab).item()
+                if graphed is not None:
+                    loss = step_fn(host_ids[i], host_lab[i]).item()       # H2D into the static buffers
+                else:
+                    loss = step_fn(host_ids[i].to(dev, non_blocking=True),
+                                   host_lab[i].to(dev, non_blocking=True)).item()
             else:
-                loss = train_step(dev_ids[i], dev_lab[i])
+                loss = step_fn(dev_ids[i], dev_lab[i])
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -281,14 +299,19 @@ def run_ours(args):
             ms = t.item()
         ev = KU.GEMM_EVENTS
         KU.GEMM_EVENTS = None
-        return ms, L.launch_count, ev, (loss if isinstance(loss, float) else float(loss.item()))
+        n_launch = L.launch_count
+        if graphed is not None and leg != "profile":
+            n_launch += graphed.launches_per_replay * args.steps
+        return ms, n_launch, ev, (loss if isinstance(loss, float) else float(loss.item()))
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_res, launches, gemm_events, loss_res = timed("resident")
+    ms_res, launches, _, loss_res = timed("resident")
     ms_e2e, _, _, loss_e2e = timed("e2e")
     clocks = sampler.stop() if rank == 0 else None
+    # roofline pass: the same K steps launched eagerly with a CUDA-event pair around every GEMM
+    ms_prof, _, gemm_events, _ = timed("profile")
     peak_vram = torch.cuda.max_memory_allocated() / 2 ** 30
 
     tokens = args.bs * args.seq * world * args.steps
@@ -311,12 +334,14 @@ def run_ours(args):
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tp):
                 traffic = json.load(open(tp)).get("gemm_kernel_dram_bytes_per_launch")
-            roof = {"bound": "tensor", "kernel": "ub::gemm::gemm_kernel<256> (tcgen05 multi-segment GEMM)",
+            roof = {"bound": "tensor", "kernel": "ub::gemm::gemm2_kernel<256> (tcgen05 cta_group::2 multi-segment GEMM; all launches >= 10 GFLOP)",
                     "achieved": round(ach, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": traffic,
                     "peak_source": peaks["src"], "launches_timed": len(big),
                     "avg_launch_ms": round(tot_ms / len(big), 4),
-                    "share_of_step": round(tot_ms / ms_res, 3)}
+                    "share_of_step": round(tot_ms / ms_prof, 3),
+                    "timing": "CUDA-event pair around every launch during an eager pass of the same %d steps "
+                              "(%.2f ms/step; events cannot be read inside a replayed graph)" % (args.steps, ms_prof / args.steps)}
 
     if rank != 0:
         return 0
@@ -337,6 +362,7 @@ def run_ours(args):
                        "global_batch": args.bs * world, "seq_len": args.seq, "parallelism": "dp%d" % world,
                        "layers": model.config.num_hidden_layers, "gradient_checkpointing": False,
                        "optimizer": "AdamW on the flat LoRA bucket (%d params)" % bucket.numel(),
+                       "cuda_graph": graph_note,
                        "l2_policy": "inputs larger than L2 (each step streams > 5 GB of NF4 weights and activations)"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 2),
                     "h2d_bytes_per_step": 2 * args.bs * args.seq * 8, "d2h_bytes_per_step": 4},
