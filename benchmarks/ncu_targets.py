@@ -37,5 +37,26 @@ elif name == "rms":
     for _ in range(3):
         L.call("ub200_rms_layernorm_fwd", L.ptr(X), H, L.ptr(W), L.BF16, L.ptr(Y), H, L.ptr(r), T, H, 1e-5, 0, L.BF16, L.stream())
         L.call("ub200_rms_layernorm_bwd", L.ptr(dY), H, L.ptr(X), H, L.ptr(W), L.BF16, L.ptr(r), L.ptr(dY), H, T, H, 0, L.BF16, L.stream())
+elif name == "rope":
+    from unsloth_b200.kernels.rope_embedding import _launch
+    B, S, Hq, Hk, D = 4, 2048, 32, 8, 128
+    q = torch.randn(B, S, Hq * D, device=DEV, dtype=BF); k = torch.randn(B, S, Hk * D, device=DEV, dtype=BF)
+    inv = 1.0 / (500000.0 ** (torch.arange(0, D, 2).float() / D)); fr = torch.outer(torch.arange(S).float(), inv)
+    emb = torch.cat([fr, fr], -1); cos, sin = emb.cos().to(DEV, BF), emb.sin().to(DEV, BF)
+    for _ in range(4):
+        _launch(q.view(B, S, Hq, D).transpose(1, 2), k.view(B, S, Hk, D).transpose(1, 2), cos, sin, None, False, True)
+elif name == "glu":
+    e = torch.randn(T, I, device=DEV, dtype=BF); g = torch.randn(T, I, device=DEV, dtype=BF); h = torch.empty_like(e)
+    for _ in range(3):
+        L.call("ub200_glu_fwd", 0, L.ptr(e), L.ptr(g), L.ptr(h), e.numel(), L.BF16, L.stream())
+        L.call("ub200_glu_bwd", 0, L.ptr(h), L.ptr(e), L.ptr(g), e.numel(), L.BF16, L.stream())
+elif name == "ce":
+    from unsloth_b200.kernels.cross_entropy_loss import _ce_backward_, _ce_forward
+    V = 128256
+    logits = torch.randn(2048, V, device=DEV, dtype=BF); labels = torch.randint(0, V, (2048,), device=DEV)
+    dl = torch.full((1,), 1e-3, device=DEV)
+    for _ in range(3):
+        l, lse = _ce_forward(logits, labels, 0.0, 0.0)
+        _ce_backward_(logits, lse, labels, dl, 0, 0.0, 0.0)
 torch.cuda.synchronize()
 print("ok")
