@@ -41,14 +41,21 @@ __global__ void __launch_bounds__(256) dequant_nf4_kernel(
     const float* __restrict__ absmax2, const float* __restrict__ offset, T* __restrict__ out,
     int64_t n, int blocksize, int blocksize2) {
   __shared__ float lut[16];
+  __shared__ int4 stage_all[8 * 32 * 4];   // 2 KB per warp, 8 warps
   if (threadIdx.x < 16) lut[threadIdx.x] = kNF4[threadIdx.x];
   __syncthreads();
   const float off = offset ? *offset : 0.f;
   const int64_t n_chunks = (n + 31) / 32;  // 32 weights per thread-chunk
-  for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunks;
-       ch += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const bool bs_ok = blocksize >= 32 && (blocksize % 32) == 0;
+  constexpr int NQ = (int)(32 * sizeof(T) / 16);        // 16-byte pieces per thread
+  // warp-uniform loop: a warp owns 32 consecutive chunks = 1024 consecutive weights
+  for (int64_t ch0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); ch0 < n_chunks;
+       ch0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ch = ch0 + lane;
     const int64_t e0 = ch * 32;
-    if (e0 + 32 <= n && blocksize >= 32 && (blocksize % 32) == 0) {
+    const bool warp_fast = bs_ok && (ch0 + 32) * 32 <= n;          // all 32 lanes have a full chunk
+    if (warp_fast) {
       const int64_t blk = e0 / blocksize;
       const float am = absmax_f32 ? absmax_f32[blk]
                                   : __fadd_rn(__fmul_rn(code2[absmax_q[blk]], absmax2[blk / blocksize2]), off);
@@ -60,10 +67,29 @@ __global__ void __launch_bounds__(256) dequant_nf4_kernel(
         o[2 * i] = cvt_out<T>(lut[b[i] >> 4] * am);
         o[2 * i + 1] = cvt_out<T>(lut[b[i] & 0xF] * am);
       }
-      int4* dst = reinterpret_cast<int4*>(out + e0);
+      if (NQ == 4) {
+        // Stage the warp's 2 KB through shared memory so that every store instruction writes 512
+        // contiguous bytes (lane l -> byte 16*l of the run) instead of 32 scattered 16-byte pieces
+        // 64 bytes apart.  Slot swizzle (piece ^ ((lane>>1)&3)) keeps both sides at the 4-wavefront
+        // minimum for 32 x 16-byte shared-memory accesses.
+        int4* stage = stage_all + (threadIdx.x >> 5) * (32 * 4);
 #pragma unroll
-      for (int i = 0; i < (int)(32 * sizeof(T) / 16); ++i) dst[i] = reinterpret_cast<int4*>(o)[i];
-    } else {
+        for (int j = 0; j < 4; ++j)
+          stage[lane * 4 + (j ^ ((lane >> 1) & 3))] = reinterpret_cast<int4*>(o)[j];
+        __syncwarp();
+        int4* dst = reinterpret_cast<int4*>(out + ch0 * 32);         // the warp's first weight
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = j * 32 + lane, src = idx >> 2, piece = idx & 3;
+          __stcs(dst + idx, stage[src * 4 + (piece ^ ((src >> 1) & 3))]);
+        }
+        __syncwarp();
+      } else {
+        int4* dst = reinterpret_cast<int4*>(out + e0);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) dst[i] = reinterpret_cast<int4*>(o)[i];
+      }
+    } else if (ch < n_chunks) {
       for (int64_t e = e0; e < n && e < e0 + 32; ++e) {
         const int64_t blk = e / blocksize;
         const float am = absmax_f32 ? absmax_f32[blk]
