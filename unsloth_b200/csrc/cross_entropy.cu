@@ -23,6 +23,11 @@ __device__ __forceinline__ float ce_transform(float x, float softcap, float scal
   return x;
 }
 
+// exp for the streaming loops: 16-bit logits use the MUFU exp2 path (relative error ~1e-6, the
+// inputs themselves carry 2^-9); fp32 logits keep the accurate expf for the 1e-5 gate.
+template <bool FAST>
+__device__ __forceinline__ float ce_exp(float x) { return FAST ? __expf(x) : expf(x); }
+
 // online logsumexp state merge
 __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
   const float nm = fmaxf(m, m2);
@@ -44,17 +49,34 @@ __global__ void __launch_bounds__(1024) ce_fwd_kernel(
     float m = -CUDART_INF_F, s = 0.f;
     if (vec_ok) {
       const int nvec = vocab / V;
-      for (int i = tid; i < nvec; i += blockDim.x) {
-        float v[V];
-        load_vec_cs<T>(x + (int64_t)i * V, v);
+      // two independent 16-byte loads in flight per thread per iteration
+      for (int i = tid; i < nvec; i += 2 * blockDim.x) {
+        float v[2][V];
+        const int i2 = i + blockDim.x;
+        const bool has2 = i2 < nvec;
+        load_vec_cs<T>(x + (int64_t)i * V, v[0]);
+        if (has2) load_vec_cs<T>(x + (int64_t)i2 * V, v[1]);
+        else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[1][k] = -CUDART_INF_F;
+        }
         float lm = -CUDART_INF_F;
 #pragma unroll
-        for (int k = 0; k < V; ++k) { v[k] = ce_transform(v[k], softcap, scale); lm = fmaxf(lm, v[k]); }
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            if (u == 0 || has2) v[u][k] = ce_transform(v[u][k], softcap, scale);
+            lm = fmaxf(lm, v[u][k]);
+          }
+        }
         const float nm = fmaxf(m, lm);
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc += expf(v[k] - nm);
-        s = s * expf(m - nm) + acc;
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc += ce_exp<sizeof(T) == 2>(v[u][k] - nm);
+        }
+        s = s * ce_exp<sizeof(T) == 2>(m - nm) + acc;
         m = nm;
       }
       for (int i = nvec * V + tid; i < vocab; i += blockDim.x) {
@@ -119,7 +141,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(
     if (scale != 0.f) xv = xv * scale;
     float partial = xv;
     if (softcap != 0.f) { partial = tanhf(xv / softcap); xv = softcap * partial; }
-    float y = expf(xv - l);
+    float y = ce_exp<sizeof(T) == 2>(xv - l);
     if (col == lab) y -= 1.0f;
     if (scale != 0.f) y *= scale;
     if (softcap != 0.f) y *= (1.0f - partial * partial);

@@ -14,11 +14,13 @@ namespace ub {
 
 enum { ACT_SWIGLU = 0, ACT_GEGLU_APPROX = 1, ACT_GEGLU_EXACT = 2 };
 
-// returns f(e) (fp32, before rounding) and df/de
-template <int ACT>
+// returns f(e) (fp32, before rounding) and df/de.  FAST (16-bit tensors): the sigmoid uses the
+// MUFU exp2 / reciprocal path (relative error ~1e-6, far below the bf16/fp16 output rounding);
+// fp32 tensors keep the accurate expf and IEEE division so the 1e-5 gate holds.
+template <int ACT, bool FAST>
 __device__ __forceinline__ void act_eval(float e, float& f, float& dfde) {
   if (ACT == ACT_SWIGLU) {
-    const float se = 1.0f / (1.0f + expf(-e));
+    const float se = FAST ? __frcp_rn(1.0f + __expf(-e)) : 1.0f / (1.0f + expf(-e));
     f = e * se;
     dfde = se * (1.0f + e * (1.0f - se));
   } else if (ACT == ACT_GEGLU_APPROX) {
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ e,
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float f, d;
-      act_eval<ACT>(ev[k], f, d);
+      act_eval<ACT, sizeof(T) == 2>(ev[k], f, d);
       o[k] = DT<T>::rnd(f) * gv[k];
     }
     store_vec<T>(h + i * V, o);
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(T* DW, T* e, T* g, int64_t
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float f, d;
-      act_eval<ACT>(ev[k], f, d);
+      act_eval<ACT, sizeof(T) == 2>(ev[k], f, d);
       const float fr = DT<T>::rnd(f);
       oh[k] = fr * gv[k];                    // h  = f * g
       odf[k] = dw[k] * fr;                   // df = DW * f
