@@ -37,7 +37,7 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
 }
 
 template <typename T>
-__global__ void __launch_bounds__(1024) ce_fwd_kernel(
+__global__ void __launch_bounds__(512, 3) ce_fwd_kernel(
     const T* __restrict__ logits, int64_t row_stride, const int64_t* __restrict__ labels,
     float* __restrict__ loss, float* __restrict__ lse_out, int64_t n_rows, int vocab,
     float softcap, float scale, int vec_ok) {
@@ -173,8 +173,10 @@ extern "C" int ub200_cross_entropy_fwd(const void* logits, int64_t row_stride,
   const int esz = dtype_size(dtype);
   const int vec_ok = (row_stride % V == 0) && (((uintptr_t)logits) % 16 == 0);
   (void)esz;
-  const int threads = vocab >= 32768 ? 1024 : (vocab >= 4096 ? 512 : 128);
-  int64_t g = (int64_t)UB_SM_COUNT * 4;
+  // 512-thread CTAs, three resident per SM: while one CTA is in its end-of-row reduction the
+  // others keep streaming (a single 1024-thread CTA per SM idled the SM at every row end)
+  const int threads = vocab >= 8192 ? 512 : (vocab >= 2048 ? 256 : 128);
+  int64_t g = (int64_t)UB_SM_COUNT * 6;
   const int grid = (int)(n_rows < g ? n_rows : g);
 #define GO(T)                                                                                  \
   ce_fwd_kernel<T><<<grid, threads, 0, stream>>>((const T*)logits, row_stride, labels, loss, lse, \
