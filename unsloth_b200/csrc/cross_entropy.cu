@@ -170,9 +170,7 @@ extern "C" int ub200_cross_entropy_fwd(const void* logits, int64_t row_stride,
   using namespace ub;
   if (n_rows <= 0) return UB200_OK;
   const int V = dtype == UB200_F32 ? 4 : 8;
-  const int esz = dtype_size(dtype);
   const int vec_ok = (row_stride % V == 0) && (((uintptr_t)logits) % 16 == 0);
-  (void)esz;
   // 512-thread CTAs, three resident per SM: while one CTA is in its end-of-row reduction the
   // others keep streaming (a single 1024-thread CTA per SM idled the SM at every row end)
   const int threads = vocab >= 8192 ? 512 : (vocab >= 2048 ? 256 : 128);

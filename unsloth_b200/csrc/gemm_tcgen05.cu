@@ -22,7 +22,6 @@
 //
 // Roofline: tensor-bound; flops = 2*M*N*sum(K_s).
 #include <cuda.h>
-#include <dlfcn.h>
 
 #include <cstring>
 #include <mutex>
@@ -38,10 +37,6 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int MAX_SEGS = UB200_GEMM_MAX_SEGMENTS;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
-
-struct SegParams {
-  int k_blocks;      // ceil(K_s / 64)
-};
 
 struct Params {
   CUtensorMap tmap_a[MAX_SEGS];
@@ -93,9 +88,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1) {

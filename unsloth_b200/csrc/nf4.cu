@@ -128,7 +128,6 @@ __global__ void __launch_bounds__(256) quant_nf4_kernel(const T* __restrict__ W,
     const float a = DT<T>::to_f(w[0]), b = DT<T>::to_f(w[1]);
     const float am = warp_max(fmaxf(fabsf(a), fabsf(b)));
     if (lane == 0) absmax[blk] = am;
-    const float inv = am > 0.f ? 1.0f / am : 0.f;
     auto nearest = [&](float v) {
       int best = 0;
       float bd = fabsf(v - kNF4[0]);
@@ -141,7 +140,6 @@ __global__ void __launch_bounds__(256) quant_nf4_kernel(const T* __restrict__ W,
     };
     // divide (not multiply by the reciprocal) to match the oracle's x / absmax
     const int qa = nearest(am > 0.f ? a / am : 0.f), qb = nearest(am > 0.f ? b / am : 0.f);
-    (void)inv;
     packed[blk * 32 + lane] = (uint8_t)((qa << 4) | qb);
   }
 }
