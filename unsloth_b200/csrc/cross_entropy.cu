@@ -37,7 +37,7 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512, 3) ce_fwd_kernel(
+__global__ void __launch_bounds__(512, 2) ce_fwd_kernel(
     const T* __restrict__ logits, int64_t row_stride, const int64_t* __restrict__ labels,
     float* __restrict__ loss, float* __restrict__ lse_out, int64_t n_rows, int vocab,
     float softcap, float scale, int vec_ok) {
@@ -49,35 +49,47 @@ __global__ void __launch_bounds__(512, 3) ce_fwd_kernel(
     float m = -CUDART_INF_F, s = 0.f;
     if (vec_ok) {
       const int nvec = vocab / V;
-      // two independent 16-byte loads in flight per thread per iteration
-      for (int i = tid; i < nvec; i += 2 * blockDim.x) {
-        float v[2][V];
+      // software-pipelined: the two 16-byte loads of iteration k+1 are issued before the exps of
+      // iteration k, so each thread always has HBM requests in flight (ncu: the unpipelined loop
+      // was latency-bound at 0.50 of peak)
+      const int step = 2 * blockDim.x;
+      int4 raw[2], nxt[2];
+      auto fetch = [&](int i, int4 (&dst)[2]) {
         const int i2 = i + blockDim.x;
-        const bool has2 = i2 < nvec;
-        load_vec_cs<T>(x + (int64_t)i * V, v[0]);
-        if (has2) load_vec_cs<T>(x + (int64_t)i2 * V, v[1]);
-        else {
+        dst[0] = (i < nvec) ? __ldcs(reinterpret_cast<const int4*>(x + (int64_t)i * V)) : make_int4(0, 0, 0, 0);
+        dst[1] = (i2 < nvec) ? __ldcs(reinterpret_cast<const int4*>(x + (int64_t)i2 * V)) : make_int4(0, 0, 0, 0);
+      };
+      fetch(tid, raw);
+      for (int i = tid; i < nvec; i += step) {
+        fetch(i + step, nxt);
+        float v[2][V];
+        const bool has2 = i + blockDim.x < nvec;
 #pragma unroll
-          for (int k = 0; k < V; ++k) v[1][k] = -CUDART_INF_F;
+        for (int u = 0; u < 2; ++u) {
+          const Vec16<T> r = *reinterpret_cast<const Vec16<T>*>(&raw[u]);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[u][k] = DT<T>::to_f(r.v[k]);
         }
         float lm = -CUDART_INF_F;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
 #pragma unroll
           for (int k = 0; k < V; ++k) {
-            if (u == 0 || has2) v[u][k] = ce_transform(v[u][k], softcap, scale);
+            v[u][k] = (u == 0 || has2) ? ce_transform(v[u][k], softcap, scale) : -CUDART_INF_F;
             lm = fmaxf(lm, v[u][k]);
           }
         }
         const float nm = fmaxf(m, lm);
-        float acc = 0.f;
+        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) acc += ce_exp<sizeof(T) == 2>(v[u][k] - nm);
+        for (int k = 0; k < V; ++k) {
+          acc0 += ce_exp<sizeof(T) == 2>(v[0][k] - nm);
+          acc1 += ce_exp<sizeof(T) == 2>(v[1][k] - nm);
         }
-        s = s * ce_exp<sizeof(T) == 2>(m - nm) + acc;
+        s = s * ce_exp<sizeof(T) == 2>(m - nm) + (acc0 + acc1);
         m = nm;
+        raw[0] = nxt[0];
+        raw[1] = nxt[1];
       }
       for (int i = nvec * V + tid; i < vocab; i += blockDim.x) {
         const float v = ce_transform(DT<T>::to_f(x[i]), softcap, scale);

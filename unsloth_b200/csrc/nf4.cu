@@ -156,7 +156,12 @@ static void launch_dequant(const uint8_t* packed, const float* absmax_f32, const
                            const float* code2, const float* absmax2, const float* offset, void* out,
                            int64_t n, int blocksize, int blocksize2, cudaStream_t st) {
   const int64_t chunks = (n + 31) / 32;
-  dequant_nf4_kernel<T><<<grid_for(chunks, 256, 16), 256, 0, st>>>(
+  static int occ = 0;       // resident CTAs per SM: launch exactly one persistent wave
+  if (!occ) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dequant_nf4_kernel<T>, 256, 0);
+    if (occ < 1) occ = 1;
+  }
+  dequant_nf4_kernel<T><<<grid_for(chunks, 256, occ), 256, 0, st>>>(
       packed, absmax_f32, absmax_q, code2, absmax2, offset, (T*)out, n, blocksize, blocksize2);
 }
 
