@@ -301,3 +301,64 @@ def test_nf4_cfg2_size_properties():
     assert err.max() < 0.2
     packed2, _ = quantize_nf4(D)
     assert (packed2 == packed).float().mean() > 0.995
+
+
+# -------------------------------------------------------------------------------------------
+# edge cases: empty inputs, ragged rows, argument errors surface as exceptions (never silently)
+# -------------------------------------------------------------------------------------------
+def test_edge_cases_empty_ragged_and_errors():
+    import unsloth_b200.kernels as K
+    H = 256
+    norm = Norm(torch.ones(H, device=DEV, dtype=torch.bfloat16), 1e-5)
+    # empty batch: nothing launched, shapes preserved
+    Y = K.fast_rms_layernorm(norm, torch.empty(0, 5, H, device=DEV, dtype=torch.bfloat16))
+    assert Y.shape == (0, 5, H)
+    assert K.swiglu_fg_kernel(torch.empty(1, 0, 64, device=DEV, dtype=torch.bfloat16),
+                              torch.empty(1, 0, 64, device=DEV, dtype=torch.bfloat16)).numel() == 0
+    # a single row / ragged row counts (not multiples of any tile)
+    for rows in (1, 3, 129, 1000):
+        X = torch.randn(rows, H, device=DEV, dtype=torch.bfloat16)
+        Yr, _ = R.rms_layernorm_fwd(X.cpu(), norm.weight.cpu(), 1e-5)
+        bf16_gate(K.fast_rms_layernorm(norm, X), Yr)
+    # hidden size that is not a multiple of the 16-byte vector -> explicit error, not garbage
+    with pytest.raises(RuntimeError, match="bad argument"):
+        K.fast_rms_layernorm(Norm(torch.ones(100, device=DEV, dtype=torch.bfloat16), 1e-5),
+                             torch.randn(4, 100, device=DEV, dtype=torch.bfloat16))
+    # GEMM operand with a leading dimension that TMA cannot address
+    A = torch.randn(64, 100, device=DEV, dtype=torch.bfloat16)      # ld = 100 (not a multiple of 8)
+    B = torch.randn(64, 100, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="bad argument"):
+        K.gemm(64, 64, [(A, B, 100)], torch.empty(64, 64, device=DEV, dtype=torch.bfloat16))
+    # mixed operand dtypes are rejected on the host side
+    with pytest.raises(RuntimeError, match="mixed operand dtypes"):
+        K.gemm(64, 64, [(A[:, :96].contiguous(), B[:, :96].contiguous().half(), 96)],
+               torch.empty(64, 64, device=DEV, dtype=torch.bfloat16))
+    # all labels ignored: loss 0 / n_items guards are the caller's (reference semantics), grads are zero
+    logits = torch.randn(1, 4, 300, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    lab = torch.full((1, 4), -100, device=DEV)
+    loss = K.fast_cross_entropy_loss(logits * 1.0, lab, n_items=1)
+    loss.backward()
+    assert loss.item() == 0 and logits.grad.abs().max().item() == 0
+
+
+def test_fp16_path_matches_oracle():
+    """fp16 activations (the reference's T4 CI dtype): RMSNorm, RoPE, SwiGLU and the GEMM."""
+    import unsloth_b200.kernels as K
+    torch.manual_seed(4)
+    X = torch.randn(5, 40, 1024).half(); W = (torch.randn(1024) * 0.2 + 1).half()
+    Yr, _ = R.rms_layernorm_fwd(X, W, 1e-5)
+    Y = K.fast_rms_layernorm(Norm(W.to(DEV), 1e-5), X.to(DEV))
+    assert (Y.float().cpu() - Yr.float()).abs().max() <= 2e-3 * Yr.float().abs().max()
+    e, g = torch.randn(1, 30, 512).half(), torch.randn(1, 30, 512).half()
+    assert (K.swiglu_fg_kernel(e.to(DEV), g.to(DEV)).float().cpu() - R.swiglu_fwd(e, g).float()).abs().max() < 4e-3
+    cos, sin = _tables(64, 64, dtype=torch.float16)
+    q, k = torch.randn(1, 20, 4 * 64).half(), torch.randn(1, 20, 2 * 64).half()
+    Qr = R.rope_noindex(q.view(1, 20, 4, 64), cos, sin).transpose(1, 2)
+    Qo, _ = K.fast_rope_embedding(q.to(DEV).view(1, 20, 4, 64).transpose(1, 2), k.to(DEV).view(1, 20, 2, 64).transpose(1, 2),
+                                  cos.to(DEV), sin.to(DEV))
+    assert (Qo.float().cpu() - Qr.float()).abs().max() < 4e-3
+    A = torch.randn(200, 256, device=DEV).half(); B = torch.randn(136, 256, device=DEV).half()
+    out = torch.empty(200, 136, device=DEV, dtype=torch.float16)
+    K.gemm(200, 136, [(A, B, 256)], out)
+    ref = A.float() @ B.float().t()
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 2e-3
