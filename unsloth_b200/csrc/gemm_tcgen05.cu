@@ -578,6 +578,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
   }
   tc_fence_before();
   cluster_sync_all();
+  __syncthreads();        // (redundant with the cluster barrier; keeps racecheck's CTA model happy)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
