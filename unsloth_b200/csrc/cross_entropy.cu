@@ -193,6 +193,12 @@ template <> struct Pk<__half> {
   __device__ static __forceinline__ T2 down(float a, float b) { return __floats2half2_rn(a, b); }
   __device__ static __forceinline__ T2 ninf() { return __float2half2_rn(-CUDART_INF_F); }
 };
+// single MUFU.EX2 (exp2f() without -use_fast_math adds denormal range handling around it)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 #define UB_LOG2E 1.4426950408889634f
 #define UB_LN2 0.6931471805599453f
 
@@ -231,11 +237,11 @@ __global__ void __launch_bounds__(512, 2) ce_fwd_lean_kernel(
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = Pk<T>::up(cur[u].h[k]);
-          a0 += exp2f(fmaf(f.x, UB_LOG2E, -nm2));
-          a1 += exp2f(fmaf(f.y, UB_LOG2E, -nm2));
+          a0 += fast_ex2(fmaf(f.x, UB_LOG2E, -nm2));
+          a1 += fast_ex2(fmaf(f.y, UB_LOG2E, -nm2));
         }
       }
-      s = s * exp2f(m2 - nm2) + (a0 + a1);
+      s = s * fast_ex2(m2 - nm2) + (a0 + a1);
       m2 = nm2;
       cur[0].q = nxt[0].q;
       cur[1].q = nxt[1].q;
@@ -243,13 +249,13 @@ __global__ void __launch_bounds__(512, 2) ce_fwd_lean_kernel(
     for (int i = nvec * 8 + tid; i < vocab; i += blockDim.x) {      // ragged tail
       const float t = DT<T>::to_f(x[i]) * UB_LOG2E;
       const float nm2 = fmaxf(m2, t);
-      s = s * exp2f(m2 - nm2) + exp2f(t - nm2);
+      s = s * fast_ex2(m2 - nm2) + fast_ex2(t - nm2);
       m2 = nm2;
     }
     auto merge = [&](float om, float os) {
       const float nm = fmaxf(m2, om);
       if (nm == -CUDART_INF_F) { s = 0.f; return; }
-      s = s * exp2f(m2 - nm) + os * exp2f(om - nm);
+      s = s * fast_ex2(m2 - nm) + os * fast_ex2(om - nm);
       m2 = nm;
     };
 #pragma unroll
@@ -297,12 +303,12 @@ __global__ void __launch_bounds__(256) ce_bwd_lean_kernel(
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = Pk<T>::up(v.h[k]);
-      o.h[k] = Pk<T>::down(dl * exp2f(fmaf(f.x, UB_LOG2E, -l2)), dl * exp2f(fmaf(f.y, UB_LOG2E, -l2)));
+      o.h[k] = Pk<T>::down(dl * fast_ex2(fmaf(f.x, UB_LOG2E, -l2)), dl * fast_ex2(fmaf(f.y, UB_LOG2E, -l2)));
     }
     const bool has_label = lab >= c && lab < c + 8;      // (softmax - 1) at the label column
     T fix = DT<T>::from_f(0.f);
     if (has_label)                                        // re-read the original logit (L1 hit)
-      fix = DT<T>::from_f(dl * (exp2f(fmaf(DT<T>::to_f(x[lab]), UB_LOG2E, -l2)) - 1.0f));
+      fix = DT<T>::from_f(dl * (fast_ex2(fmaf(DT<T>::to_f(x[lab]), UB_LOG2E, -l2)) - 1.0f));
     *reinterpret_cast<int4*>(x + c) = o.q;
     if (has_label) x[lab] = fix;                          // same thread, program order: lands last
   }
