@@ -42,6 +42,7 @@ struct Params {
   CUtensorMap tmap_a[MAX_SEGS];
   CUtensorMap tmap_b[MAX_SEGS];
   int seg_kblocks[MAX_SEGS];
+  int seg_k[MAX_SEGS];     // true K of the segment: UMMA_K steps past it are skipped
   int n_segs;
   int M, N;
   int a_mn, b_mn;        // operand majors (uniform over segments)
@@ -453,7 +454,12 @@ gemm_kernel(const __grid_constant__ Params p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        int seg = 0, seg_start = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          while (kb >= seg_start + p.seg_kblocks[seg]) { seg_start += p.seg_kblocks[seg]; ++seg; }
+          // UMMA_K steps that hold real data in this k-block (rank blocks and K tails are zero-padded)
+          const int k_left = p.seg_k[seg] - (kb - seg_start) * BLOCK_K;
+          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -462,8 +468,9 @@ gemm_kernel(const __grid_constant__ Params p) {
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            if (k < ksteps)
+              umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -648,7 +655,11 @@ gemm2_kernel(const __grid_constant__ Params p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        int seg = 0, seg_start = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          while (kb >= seg_start + p.seg_kblocks[seg]) { seg_start += p.seg_kblocks[seg]; ++seg; }
+          const int k_left = p.seg_k[seg] - (kb - seg_start) * BLOCK_K;
+          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -657,8 +668,9 @@ gemm2_kernel(const __grid_constant__ Params p) {
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
-                         (kb > kb0 || k > 0) ? 1u : 0u);
+            if (k < ksteps)
+              umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar(stage));      // frees the stage in BOTH CTAs
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -843,6 +855,7 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     const ub200_gemm_segment& g = segs[s];
     if (g.k <= 0) return UB200_ERR_BAD_ARG;
     p.seg_kblocks[s] = (int)((g.k + BLOCK_K - 1) / BLOCK_K);
+    p.seg_k[s] = (int)g.k;
     total_kb += p.seg_kblocks[s];
     int rc;
     if (!p.a_mn) rc = make_tmap(&p.tmap_a[s], g.a, M, g.k, g.lda, BLOCK_M, p.ab_fp16);

@@ -123,7 +123,7 @@ class _Group:
                     B_pad = cached_cast_pad(Bc, (self.Rp, N), dt, row_off=off, scale=s, transpose=True)
                 else:
                     B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s)
-                segs.append((XA, B_pad, self.Rp))
+                segs.append((XA, B_pad, self.rank_total))   # true rank: padded UMMA_K steps are skipped
             Y = torch.empty((T, N), dtype=dt, device=dev)
             gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
             outs.append(Y)
@@ -176,7 +176,7 @@ class _Group:
                 Bop, b_mn = Bop.t().contiguous(), True
             segs.append((dY, Bop, dY.shape[1]))
         if self.has_lora:
-            segs.append((G, self.A_cat(), Rp))
+            segs.append((G, self.A_cat(), self.rank_total))
         dX = dX_out if dX_out is not None else torch.empty((T, self.in_f), dtype=dt, device=dev)
         gemm(T, self.in_f, segs, dX, a_mn=False, b_mn=True)
         return dX, grads
@@ -236,7 +236,7 @@ class LoRA_MLP(torch.autograd.Function):
             BT_pad = cached_cast_pad(Bc, (down.Rp, Bc.shape[0]), dt, scale=downS, transpose=True)
             G_down = gemm(T, down.Rp, [(dY2, BT_pad, Bc.shape[0])],
                           torch.empty((T, down.Rp), dtype=dt, device=dev))
-            segs.append((G_down, down.A_cat(), down.Rp))
+            segs.append((G_down, down.A_cat(), down.rank_total))
         DW = torch.empty((T, e.shape[1]), dtype=dt, device=dev)
         gemm(T, e.shape[1], segs, DW, a_mn=False, b_mn=True)
         # --- activation backward, in place: DW <- h, e <- df, g <- de            (:156-157)
