@@ -23,6 +23,7 @@
 // Roofline: tensor-bound; flops = 2*M*N*sum(K_s).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -840,6 +841,7 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
   bool pair = cta_group == 2 || (cta_group == 0 && bn >= 128 && M > BLOCK_M);
   if (pair && bn < 128) return UB200_ERR_BAD_ARG;
 
+  static const bool full_ksteps = getenv("UB200_GEMM_FULL_KSTEPS") != nullptr;   // A/B switch
   Params p;
   memset(&p, 0, sizeof(p));
   p.n_segs = n_segs;
@@ -855,7 +857,7 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     const ub200_gemm_segment& g = segs[s];
     if (g.k <= 0) return UB200_ERR_BAD_ARG;
     p.seg_kblocks[s] = (int)((g.k + BLOCK_K - 1) / BLOCK_K);
-    p.seg_k[s] = (int)g.k;
+    p.seg_k[s] = full_ksteps ? p.seg_kblocks[s] * BLOCK_K : (int)g.k;
     total_kb += p.seg_kblocks[s];
     int rc;
     if (!p.a_mn) rc = make_tmap(&p.tmap_a[s], g.a, M, g.k, g.lda, BLOCK_M, p.ab_fp16);
