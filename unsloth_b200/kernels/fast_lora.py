@@ -137,16 +137,18 @@ class _Group:
         grads = []
         G = None
         if self.has_lora:
-            # G[T, Rp] = sum_i dY_i @ (s_i B_i) placed at the adapter's rank slot
+            # G[T, Rp] = sum_i dY_i @ (s_i B_i) placed at the adapter's rank slot.  The B operand
+            # is the SAME zero-padded [out_i, Rp] block the forward used, consumed MN-major
+            # ([K=out_i, N=Rp] row-major): no transposed copy of B is ever made.
             segs = []
             for off, dY, (W, Wq, A, B, s) in zip(self.offs, dYs, self.projs):
                 if A is None:
                     continue
                 Bc = B if B.stride(-1) == 1 else B.contiguous()
                 out_f = Bc.shape[0]
-                BT_pad = cached_cast_pad(Bc, (Rp, out_f), dt, row_off=off, scale=s, transpose=True)
-                segs.append((dY, BT_pad, out_f))
-            G = gemm(T, Rp, segs, torch.empty((T, Rp), dtype=dt, device=dev))
+                B_pad = cached_cast_pad(Bc, (out_f, Rp), dt, col_off=off, scale=s)
+                segs.append((dY, B_pad, out_f))
+            G = gemm(T, Rp, segs, torch.empty((T, Rp), dtype=dt, device=dev), b_mn=True)
             # dA_cat^T [in, Rp] = X^T @ G   (both operands MN-major, reduction over tokens)
             dA_catT = torch.empty((self.in_f, Rp), dtype=torch.float32, device=dev)
             gemm(self.in_f, Rp, [(X2, G, T)], dA_catT, a_mn=True, b_mn=True,
@@ -235,9 +237,9 @@ class LoRA_MLP(torch.autograd.Function):
         segs.append((dY2, Bop, dY2.shape[1]))
         if downA is not None:
             Bc = downB if downB.stride(-1) == 1 else downB.contiguous()
-            BT_pad = cached_cast_pad(Bc, (down.Rp, Bc.shape[0]), dt, scale=downS, transpose=True)
-            G_down = gemm(T, down.Rp, [(dY2, BT_pad, Bc.shape[0])],
-                          torch.empty((T, down.Rp), dtype=dt, device=dev))
+            B_pad = cached_cast_pad(Bc, (Bc.shape[0], down.Rp), dt, scale=downS)     # as in forward
+            G_down = gemm(T, down.Rp, [(dY2, B_pad, Bc.shape[0])],
+                          torch.empty((T, down.Rp), dtype=dt, device=dev), b_mn=True)
             segs.append((G_down, down.A_cat(), down.Rp if _PAD_K else down.rank_total))
         DW = torch.empty((T, e.shape[1]), dtype=dt, device=dev)
         gemm(T, e.shape[1], segs, DW, a_mn=False, b_mn=True)
