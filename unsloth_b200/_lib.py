@@ -14,7 +14,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libunsloth_b200.so")
+LIB_PATH = os.environ.get("UB200_LIB_PATH") or os.path.join(_HERE, "_C", "libunsloth_b200.so")   # override: A/B builds
 
 F32, F16, BF16 = 0, 1, 2
 ACT_SWIGLU, ACT_GEGLU_APPROX, ACT_GEGLU_EXACT = 0, 1, 2
