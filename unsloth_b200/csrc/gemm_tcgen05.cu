@@ -23,7 +23,6 @@
 // Roofline: tensor-bound; flops = 2*M*N*sum(K_s).
 #include <cuda.h>
 
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -43,8 +42,6 @@ struct Params {
   CUtensorMap tmap_a[MAX_SEGS];
   CUtensorMap tmap_b[MAX_SEGS];
   int seg_kblocks[MAX_SEGS];
-  int seg_end_kb[MAX_SEGS + 1];  // cumulative k-block index one past each segment (last entry: sentinel)
-  int seg_last_ksteps[MAX_SEGS]; // UMMA_K steps holding real data in the segment's LAST k-block (1..4)
   int n_segs;
   int M, N;
   int a_mn, b_mn;        // operand majors (uniform over segments)
@@ -456,20 +453,7 @@ gemm_kernel(const __grid_constant__ Params p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        // Only the LAST k-block of a segment can be partial (LoRA rank blocks and K tails are
-        // zero-padded to 64): track the next segment boundary in registers so that the issuing
-        // thread touches the parameter block only when it crosses one.
-        int seg = 0;
-        while (p.seg_end_kb[seg] <= kb0) ++seg;
-        int next_end = p.seg_end_kb[seg], last_steps = p.seg_last_ksteps[seg];
         for (int kb = kb0; kb < kb1; ++kb) {
-          int ksteps = BLOCK_K / UMMA_K;
-          if (kb + 1 == next_end) {
-            ksteps = last_steps;
-            ++seg;
-            next_end = p.seg_end_kb[seg];
-            last_steps = p.seg_last_ksteps[seg < MAX_SEGS ? seg : MAX_SEGS - 1];
-          }
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -478,9 +462,8 @@ gemm_kernel(const __grid_constant__ Params p) {
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (k < ksteps)
-              umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
-                       (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -665,17 +648,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        int seg = 0;
-        while (p.seg_end_kb[seg] <= kb0) ++seg;
-        int next_end = p.seg_end_kb[seg], last_steps = p.seg_last_ksteps[seg];
         for (int kb = kb0; kb < kb1; ++kb) {
-          int ksteps = BLOCK_K / UMMA_K;
-          if (kb + 1 == next_end) {
-            ksteps = last_steps;
-            ++seg;
-            next_end = p.seg_end_kb[seg];
-            last_steps = p.seg_last_ksteps[seg < MAX_SEGS ? seg : MAX_SEGS - 1];
-          }
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -684,9 +657,8 @@ gemm2_kernel(const __grid_constant__ Params p) {
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (k < ksteps)
-              umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
-                           (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar(stage));      // frees the stage in BOTH CTAs
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -856,7 +828,6 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
   bool pair = cta_group == 2 || (cta_group == 0 && bn >= 128 && M > BLOCK_M);
   if (pair && bn < 128) return UB200_ERR_BAD_ARG;
 
-  static const bool full_ksteps = getenv("UB200_GEMM_FULL_KSTEPS") != nullptr;   // A/B switch
   Params p;
   memset(&p, 0, sizeof(p));
   p.n_segs = n_segs;
@@ -872,12 +843,7 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     const ub200_gemm_segment& g = segs[s];
     if (g.k <= 0) return UB200_ERR_BAD_ARG;
     p.seg_kblocks[s] = (int)((g.k + BLOCK_K - 1) / BLOCK_K);
-    {
-      const int rem = (int)(g.k - (int64_t)(p.seg_kblocks[s] - 1) * BLOCK_K);       // 1..64
-      p.seg_last_ksteps[s] = full_ksteps ? BLOCK_K / UMMA_K : (rem + UMMA_K - 1) / UMMA_K;
-    }
     total_kb += p.seg_kblocks[s];
-    p.seg_end_kb[s] = total_kb;
     int rc;
     if (!p.a_mn) rc = make_tmap(&p.tmap_a[s], g.a, M, g.k, g.lda, BLOCK_M, p.ab_fp16);
     else         rc = make_tmap(&p.tmap_a[s], g.a, g.k, M, g.lda, 64, p.ab_fp16);
@@ -886,7 +852,6 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     else         rc = make_tmap(&p.tmap_b[s], g.b, g.k, N, g.ldb, 64, p.ab_fp16);
     if (rc) return rc;
   }
-  for (int s = n_segs; s <= MAX_SEGS; ++s) p.seg_end_kb[s] = 0x7fffffff;     // sentinels
   if (split_k > total_kb) split_k = total_kb;
   p.split_k = split_k;
   p.alpha = alpha;

@@ -27,8 +27,6 @@ from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
                     geglu_approx_forward_kernel, geglu_approx_backward_kernel)
 
 _SM = 148
-import os as _os
-_PAD_K = _os.environ.get("UB200_LORA_PAD_K") is not None      # A/B switch: pass the padded rank as K
 
 
 def _epoch():
@@ -125,7 +123,7 @@ class _Group:
                     B_pad = cached_cast_pad(Bc, (self.Rp, N), dt, row_off=off, scale=s, transpose=True)
                 else:
                     B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s)
-                segs.append((XA, B_pad, self.Rp if _PAD_K else self.rank_total))   # true rank: padded UMMA_K steps are skipped
+                segs.append((XA, B_pad, self.Rp))
             Y = torch.empty((T, N), dtype=dt, device=dev)
             gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
             outs.append(Y)
@@ -180,7 +178,7 @@ class _Group:
                 Bop, b_mn = Bop.t().contiguous(), True
             segs.append((dY, Bop, dY.shape[1]))
         if self.has_lora:
-            segs.append((G, self.A_cat(), Rp if _PAD_K else self.rank_total))
+            segs.append((G, self.A_cat(), Rp))
         dX = dX_out if dX_out is not None else torch.empty((T, self.in_f), dtype=dt, device=dev)
         gemm(T, self.in_f, segs, dX, a_mn=False, b_mn=True)
         return dX, grads
@@ -240,7 +238,7 @@ class LoRA_MLP(torch.autograd.Function):
             B_pad = cached_cast_pad(Bc, (Bc.shape[0], down.Rp), dt, scale=downS)     # as in forward
             G_down = gemm(T, down.Rp, [(dY2, B_pad, Bc.shape[0])],
                           torch.empty((T, down.Rp), dtype=dt, device=dev), b_mn=True)
-            segs.append((G_down, down.A_cat(), down.Rp if _PAD_K else down.rank_total))
+            segs.append((G_down, down.A_cat(), down.Rp))
         DW = torch.empty((T, e.shape[1]), dtype=dt, device=dev)
         gemm(T, e.shape[1], segs, DW, a_mn=False, b_mn=True)
         # --- activation backward, in place: DW <- h, e <- df, g <- de            (:156-157)

@@ -208,7 +208,7 @@ def matmul_lora(X, W, W_quant, A, B, s, out=None):
                              transpose=True)
         else:
             B_pad = cast_pad(B, torch.empty((N, Rp), dtype=dtype, device=X.device), scale=s)
-        segs.append((XA, B_pad, r))        # true rank: the zero-padded UMMA_K steps are skipped
+        segs.append((XA, B_pad, Rp))
     gemm(T, N, segs, out2, a_mn=False, b_mn=b_mn)
     return out2.view(batch, seq_len, -1) if reshape else out2
 
