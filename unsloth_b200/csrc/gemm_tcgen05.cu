@@ -86,6 +86,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// One leader lane of a converged warp.  Issuing TMA / tcgen05 instructions under `elect.sync`
+// inside WARP-UNIFORM control flow lets ptxas keep descriptors and barrier addresses in uniform
+// registers; issuing them under `if (lane == 0)` made it wrap every UTCHMMA / UTMALDG in an
+// ELECT + R2UR.BROADCAST waterfall loop (~25 extra instructions per MMA on the single issuing
+// thread -- round-1 SASS reading, profiles/README.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -402,7 +418,7 @@ gemm_kernel(const __grid_constant__ Params p) {
 
   if (warp == 0) {
     // ================================ TMA producer ===================================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -416,28 +432,31 @@ gemm_kernel(const __grid_constant__ Params p) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          if (!p.a_mn) {
-            tma_load_2d(sa, &p.tmap_a[seg], full_bar(stage), k0, m_blk * BLOCK_M);
-          } else {
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(sa, &p.tmap_a[seg], full_bar(stage), k0, m_blk * BLOCK_M);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(sa + j * 8192u, &p.tmap_a[seg], full_bar(stage), m_blk * BLOCK_M + j * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &p.tmap_b[seg], full_bar(stage), k0, n_blk * BLOCK_N);
-          } else {
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d(sa + j * 8192u, &p.tmap_a[seg], full_bar(stage), m_blk * BLOCK_M + j * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &p.tmap_b[seg], full_bar(stage), k0, n_blk * BLOCK_N);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * 8192u, &p.tmap_b[seg], full_bar(stage), n_blk * BLOCK_N + j * 64, k0);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(sb + j * 8192u, &p.tmap_b[seg], full_bar(stage), n_blk * BLOCK_N + j * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer =====================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, p.a_mn, p.b_mn, p.ab_fp16);
       // per-UMMA_K advance of the descriptor start address (in 16-byte units)
       const uint32_t a_adv = p.a_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
@@ -460,15 +479,22 @@ gemm_kernel(const __grid_constant__ Params p) {
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t da = make_smem_desc(sa, a_lbo, 1024u);
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_f16(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));        // frees the smem stage when the MMAs retire
+            if (kb == kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator ready for the epilogue
           }
-          umma_commit(empty_bar(stage));          // frees the smem stage when the MMAs retire
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator ready for the epilogue
+        if (kb1 <= kb0) {                         // empty split: still hand the buffer over
+          if (elect_one()) umma_commit(tfull_bar(acc));
+          __syncwarp();
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -595,7 +621,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) =======================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = pair; w < num_work; w += num_pairs) {
@@ -611,29 +637,32 @@ gemm2_kernel(const __grid_constant__ Params p) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
-          else mbar_arrive_remote(full_bar(stage), 0u);
-          if (!p.a_mn) {
-            tma_load_2d_2sm(sa, &p.tmap_a[seg], full_bar(stage), k0, m0);
-          } else {
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
+            else mbar_arrive_remote(full_bar(stage), 0u);
+            if (!p.a_mn) {
+              tma_load_2d_2sm(sa, &p.tmap_a[seg], full_bar(stage), k0, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d_2sm(sa + j * 8192u, &p.tmap_a[seg], full_bar(stage), m0 + j * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d_2sm(sb, &p.tmap_b[seg], full_bar(stage), k0, n0);
-          } else {
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d_2sm(sa + j * 8192u, &p.tmap_a[seg], full_bar(stage), m0 + j * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_2sm(sb, &p.tmap_b[seg], full_bar(stage), k0, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < C::HALF_N / 64; ++j)
-              tma_load_2d_2sm(sb + j * 8192u, &p.tmap_b[seg], full_bar(stage), n0 + j * 64, k0);
+              for (int j = 0; j < C::HALF_N / 64; ++j)
+                tma_load_2d_2sm(sb + j * 8192u, &p.tmap_b[seg], full_bar(stage), n0 + j * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ===================
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       const uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N, p.a_mn, p.b_mn, p.ab_fp16);
       const uint32_t a_adv = p.a_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
       const uint32_t b_adv = p.b_mn ? (UMMA_K * 128u) >> 4 : (UMMA_K * 2u) >> 4;
@@ -655,15 +684,22 @@ gemm2_kernel(const __grid_constant__ Params p) {
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t da = make_smem_desc(sa, a_lbo, 1024u);
           const uint64_t db = make_smem_desc(sb, b_lbo, 1024u);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
-                         (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_f16_2sm(d_tmem, da + (uint64_t)(a_adv * k), db + (uint64_t)(b_adv * k), idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(empty_bar(stage));      // frees the stage in BOTH CTAs
+            if (kb == kb1 - 1) umma_commit_2sm(tfull_bar(acc));   // accumulator ready in BOTH CTAs
           }
-          umma_commit_2sm(empty_bar(stage));      // frees the stage in BOTH CTAs
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_2sm(tfull_bar(acc));          // accumulator ready in BOTH CTAs
+        if (kb1 <= kb0) {
+          if (elect_one()) umma_commit_2sm(tfull_bar(acc));
+          __syncwarp();
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
