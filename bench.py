@@ -131,7 +131,22 @@ def cpu_reference_tokens_per_sec(model_name, seq_tokens, r=RANK_R, threads=None,
     from torch import nn
     from unsloth_b200.patch import hf_config, CONFIGS
 
-    threads = threads or os.cpu_count() or 1
+    if threads is None:
+        # use the thread count at which this host's torch CPU GEMM is actually fastest (on many-core
+        # hosts "all cores" can be slower than a subset): probe a projection-sized matmul
+        cores = os.cpu_count() or 1
+        a, b = torch.randn(seq_tokens, 4096), torch.randn(4096, 4096)
+        best_t, best = cores, None
+        for cand in sorted({cores, max(1, cores // 2), min(cores, 64), min(cores, 32)}, reverse=True):
+            torch.set_num_threads(cand)
+            a @ b
+            t0 = time.perf_counter()
+            for _ in range(3):
+                a @ b
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, best_t = dt, cand
+        threads = best_t
     torch.set_num_threads(threads)
     full_layers = CONFIGS[model_name]["num_hidden_layers"]
 
