@@ -2,7 +2,6 @@
 flash-attn 2 vs torch SDPA backends (cuDNN / flash / efficient), fwd and fwd+bwd, on the strided
 [B,S,H,D] projection-buffer views the model uses."""
 import json
-import sys
 
 import torch
 import torch.nn.functional as F

@@ -4,8 +4,6 @@
 """
 from __future__ import annotations
 
-import ctypes
-
 import torch
 
 from .. import _lib as L

@@ -25,7 +25,6 @@ import types
 from types import SimpleNamespace
 
 import torch
-from torch import nn
 
 from . import kernels as K
 from .lora import LoraLinear
