@@ -59,6 +59,19 @@ int ub200_rms_layernorm_bwd(const void* dY, int64_t dy_row_stride, const void* X
                             void* dX, int64_t dx_row_stride, int64_t n_rows, int n_cols, int gemma,
                             int dtype, cudaStream_t stream);
 
+/* Residual add fused with the following RMSNorm (models/llama.py:838-844 does `residual +
+ * hidden_states` and fast_rms_layernorm as two passes): S = A + B, Y = RMSNorm(S) * W, r[T].
+ * Backward companion: dS += rms_bwd(dY, S, W, r), accumulated in place into the residual-stream
+ * gradient.  16-bit activations with weights of the same dtype (Llama / Mistral form).           */
+int ub200_add_rms_layernorm_fwd(const void* A, int64_t a_row_stride, const void* B,
+                                int64_t b_row_stride, const void* W, void* S, int64_t s_row_stride,
+                                void* Y, int64_t y_row_stride, float* r, int64_t n_rows, int n_cols,
+                                float eps, int dtype, cudaStream_t stream);
+int ub200_rms_layernorm_bwd_acc(const void* dY, int64_t dy_row_stride, const void* X,
+                                int64_t x_row_stride, const void* W, const float* r, void* dS,
+                                int64_t ds_row_stride, int64_t n_rows, int n_cols, int dtype,
+                                cudaStream_t stream);
+
 /* ---- RoPE -----------------------------------------------------------------------------------
  * fast_rope_embedding (unsloth/kernels/rope_embedding.py:265-280): Fast_RoPE_Embedding (:169-261)
  * and Fast_RoPE_Embedding_QK (:283-399) as ONE strided in-place kernel over Q and K.

@@ -82,6 +82,46 @@ def test_rmsnorm_bf16_vs_oracle(gemma, H):
         assert Xg.grad.data_ptr() == dYg.data_ptr()
 
 
+@pytest.mark.parametrize("H,dt", [(4096, torch.bfloat16), (2048, torch.bfloat16), (256, torch.float16),
+                                  (8192, torch.bfloat16)])
+def test_add_rmsnorm_fused_vs_oracle_and_separate_ops(H, dt):
+    """Residual add fused with the next RMSNorm: S and Y are BIT-EXACT against the two separate
+    ops (torch's 16-bit add, then fast_rms_layernorm); the backward (norm gradient accumulated in
+    place into the residual gradient) against the oracle's rms_layernorm_bwd + dS in fp32."""
+    from unsloth_b200.kernels import fast_add_rms_layernorm, fast_rms_layernorm
+    torch.manual_seed(11)
+    A = torch.randn(2, 45, H).to(dt)
+    B = (torch.randn(2, 45, H) * 0.5).to(dt)
+    W = (torch.randn(H) * 0.3 + 1).to(dt)
+    dS = torch.randn(2, 45, H).to(dt)
+    dY = torch.randn(2, 45, H).to(dt)
+    Ag, Bg = A.to(DEV).requires_grad_(), B.to(DEV).requires_grad_()
+    norm = Norm(W.to(DEV), 1e-5)
+    S, Y = fast_add_rms_layernorm(norm, Ag, Bg)
+    S_sep = A.to(DEV) + B.to(DEV)
+    Y_sep = fast_rms_layernorm(norm, S_sep)
+    assert torch.equal(S, S_sep) and torch.equal(Y, Y_sep)
+    Sr = A + B                                             # oracle: torch CPU add, one rounding
+    assert torch.equal(S.cpu(), Sr)
+    Yr, r = R.rms_layernorm_fwd(Sr, W, 1e-5, False)
+    bf16_gate(Y, Yr)
+    dSg = dS.to(DEV).clone()
+    torch.autograd.backward([S, Y], [dSg, dY.to(DEV).clone()])
+    ref = dS.float() + R.rms_layernorm_bwd(dY.float(), Sr, W, r, False).float()
+    bf16_gate(Ag.grad, ref)
+    assert torch.equal(Ag.grad, Bg.grad)
+    assert torch.equal(dSg, Ag.grad)                       # accumulated in place into dS
+    # S unused downstream (last norm of the stack): plain norm backward
+    A2, B2 = A.to(DEV).requires_grad_(), B.to(DEV).requires_grad_()
+    _, Y2 = fast_add_rms_layernorm(norm, A2, B2)
+    Y2.backward(dY.to(DEV).clone())
+    bf16_gate(A2.grad, R.rms_layernorm_bwd(dY, Sr, W, r, False))
+    # fp32 activations fall back to the two separate ops (same results as fast_rms_layernorm)
+    S3, Y3 = fast_add_rms_layernorm(Norm(W.float().to(DEV), 1e-5), A.float().to(DEV), B.float().to(DEV))
+    Y3r, _ = R.rms_layernorm_fwd(A.float() + B.float(), W.float(), 1e-5, False)
+    close(Y3, Y3r)
+
+
 def test_rmsnorm_cfg2_properties():
     """Full cfg2 size (T=8192, H=4096): unit RMS of the output for W=1 and scale invariance."""
     from unsloth_b200.kernels import fast_rms_layernorm

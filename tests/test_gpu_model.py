@@ -92,6 +92,76 @@ def test_patched_model_matches_reference_cpu_path(name, extra, seq):
     assert worst > 0.98
 
 
+@pytest.mark.parametrize("name", ["llama-3-8b", "mistral-7b-v0.3"])
+def test_fused_add_norm_stack_matches_layerwise_form(name):
+    """The Llama/Mistral stack with every residual add fused into the following RMSNorm
+    (patch.FUSE_ADD_NORM) against the layer-by-layer form of models/llama.py:823-844: the forward is
+    bit-identical (same loss); gradients differ only by the one bf16 rounding the fusion removes."""
+    import unsloth_b200.patch as P
+    model = P.build_qlora_model(name, r=8, lora_alpha=16, device=DEV, num_hidden_layers=3,
+                                init_b_std=0.05, **TINY)
+    torch.manual_seed(5)
+    ids = torch.randint(0, TINY["vocab_size"], (2, 96), device=DEV)
+    res = {}
+    try:
+        for fuse in (True, False):
+            P.FUSE_ADD_NORM = fuse
+            for p_ in P.lora_parameters(model):
+                p_.grad = None
+            loss = model(input_ids=ids, labels=ids).loss
+            loss.backward()
+            res[fuse] = (loss.item(), [p_.grad.float().clone() for p_ in P.lora_parameters(model)])
+    finally:
+        P.FUSE_ADD_NORM = True
+    assert res[True][0] == res[False][0]
+    for a, b in zip(res[True][1], res[False][1]):
+        cos = torch.dot(a.flatten(), b.flatten()) / (a.norm() * b.norm() + 1e-30)
+        assert cos > 0.999, cos.item()
+        assert abs(a.norm().item() / (b.norm().item() + 1e-30) - 1) < 0.02
+
+
+@pytest.mark.parametrize("name,extra", [("llama-3-8b", {}), ("mistral-7b-v0.3", {"sliding_window": 32}),
+                                        ("gemma-2-9b", {"query_pre_attn_scalar": 64, "sliding_window": 32})])
+def test_packed_row_equals_separate_documents(name, extra):
+    """Packed / padding-free path (llama.py:706-730, attention_dispatch.py:433-447):
+    one flattened row holding two documents, with `packed_seq_lengths`, must give each document
+    the hidden states and the loss it gets alone (no attention across the boundary, RoPE restarted,
+    boundary target masked), and the token-weighted mean of the per-document losses."""
+    from unsloth_b200.patch import build_qlora_model, lora_parameters
+    kw = dict(TINY, **extra)
+    model = build_qlora_model(name, r=8, lora_alpha=16, device=DEV, num_hidden_layers=2,
+                              init_b_std=0.05, **kw)
+    torch.manual_seed(9)
+    L1, L2 = 40, 88
+    d1 = torch.randint(0, kw["vocab_size"], (1, L1), device=DEV)
+    d2 = torch.randint(0, kw["vocab_size"], (1, L2), device=DEV)
+    row = torch.cat([d1, d2], 1)
+    lens = torch.tensor([L1, L2], dtype=torch.int32)
+    with torch.no_grad():
+        hp = model(input_ids=row, packed_seq_lengths=lens).hidden_states.float()
+        h1 = model(input_ids=d1).hidden_states.float()
+        h2 = model(input_ids=d2).hidden_states.float()
+        leaked = model(input_ids=row).hidden_states.float()
+    scale = h2.abs().max().item()
+    assert (hp[:, :L1] - h1).abs().max().item() < 3e-2 * scale
+    assert (hp[:, L1:] - h2).abs().max().item() < 3e-2 * scale
+    assert (leaked[:, L1:] - h2).abs().max().item() > 0.1 * scale      # the test can tell
+    grads = {}
+    for key, batches in (("packed", [(row, lens)]), ("separate", [(d1, None), (d2, None)])):
+        for p_ in lora_parameters(model):
+            p_.grad = None
+        total = 0.0
+        for ids, pl in batches:
+            loss = model(input_ids=ids, labels=ids, packed_seq_lengths=pl,
+                         num_items_in_batch=L1 + L2 - 2).loss
+            loss.backward()
+            total += loss.item()
+        grads[key] = (total, torch.cat([p_.grad.float().flatten() for p_ in lora_parameters(model)]))
+    assert abs(grads["packed"][0] - grads["separate"][0]) < 5e-3 * abs(grads["separate"][0])
+    a, b = grads["packed"][1], grads["separate"][1]
+    assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.995
+
+
 def test_sliding_window_and_softcap_route():
     """Mistral / Gemma-2 deltas go through flash-attn with the reference's arguments
     (mistral.py:112-128, gemma2.py:159): check against an explicit masked softmax."""

@@ -1,0 +1,55 @@
+"""Host logic of the packed / padding-free path against the values the
+reference's own tests pin (tests/utils/test_packing.py:1489-1525, :1545-1572, :1575-1584) and the
+metadata contract of unsloth/utils/packing.py:586-606."""
+import torch
+
+from unsloth_b200.packing import (clear_packed_caches, get_packed_info_from_kwargs,
+                                  mask_packed_boundary_labels, num_items_in_batch,
+                                  packed_position_ids)
+
+
+def test_boundary_mask_values_pinned_by_reference_tests():
+    labels = torch.arange(8, dtype=torch.long).view(1, 8)
+    out = mask_packed_boundary_labels(labels, torch.tensor([3, 5], dtype=torch.int32))
+    # the shifted view the CE sees must be [1,2,-100,4,5,6,7] (test_packing.py:1522)
+    assert out.reshape(-1).tolist() == [-100, 1, 2, -100, 4, 5, 6, 7]
+    assert labels.reshape(-1).tolist() == list(range(8))          # out of place
+    lengths = torch.tensor([2, 1, 3], dtype=torch.int32)
+    once = mask_packed_boundary_labels(torch.arange(6).view(1, 6), lengths)
+    assert once.reshape(-1).tolist() == [-100, 1, -100, -100, 4, 5]   # :1584
+    assert torch.equal(mask_packed_boundary_labels(once, lengths), once)
+    assert mask_packed_boundary_labels(labels, None) is labels
+    assert mask_packed_boundary_labels(labels, torch.tensor([], dtype=torch.int32)) is labels
+
+
+def test_num_items_rule():
+    # docs [10,11] [12] [13,14,15] -> 1 + 0 + 2 real CE targets (test_packing.py:1557-1572)
+    labels = torch.tensor([[10, 11, 12, 13, 14, 15]])
+    assert num_items_in_batch(labels, torch.tensor([2, 1, 3], dtype=torch.int32)) == 3
+    assert num_items_in_batch(labels) == 5
+    masked = mask_packed_boundary_labels(labels, torch.tensor([2, 1, 3]))
+    assert int((masked[..., 1:] != -100).sum()) == 3               # the mask and the rule agree
+
+
+def test_packed_info_and_position_ids():
+    clear_packed_caches()
+    lens = torch.tensor([3, 5], dtype=torch.int32)
+    kw = {"packed_seq_lengths": lens}
+    lengths, cu, mx = get_packed_info_from_kwargs(kw, "cpu")
+    assert lengths.dtype == torch.int32 and cu.dtype == torch.int32
+    assert cu.tolist() == [0, 3, 8] and mx == 5
+    assert get_packed_info_from_kwargs(kw, "cpu")[1] is cu          # cached on tensor identity
+    assert get_packed_info_from_kwargs({}, "cpu") is None
+    assert packed_position_ids(lens).tolist() == [0, 1, 2, 0, 1, 2, 3, 4]
+    # trailing pad tokens: one more segment so the boundaries cover the flattened row
+    clear_packed_caches()
+    _, cu2, mx2 = get_packed_info_from_kwargs(kw, "cpu", total=10)
+    assert cu2.tolist() == [0, 3, 8, 10] and mx2 == 5
+    assert packed_position_ids(lens, 10).tolist() == [0, 1, 2, 0, 1, 2, 3, 4, 0, 1]
+    try:
+        clear_packed_caches()
+        get_packed_info_from_kwargs(kw, "cpu", total=7)
+        assert False, "over-long lengths must raise"
+    except ValueError:
+        pass
+    clear_packed_caches()

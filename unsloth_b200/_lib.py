@@ -52,6 +52,8 @@ _SIGS = {
     "ub200_abi_version": ([], c_int),
     "ub200_rms_layernorm_fwd": ([_p, _l, _p, _i, _p, _l, _p, _l, _i, _f, _i, _i, _p], c_int),
     "ub200_rms_layernorm_bwd": ([_p, _l, _p, _l, _p, _i, _p, _p, _l, _l, _i, _i, _i, _p], c_int),
+    "ub200_add_rms_layernorm_fwd": ([_p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _i, _f, _i, _p], c_int),
+    "ub200_rms_layernorm_bwd_acc": ([_p, _l, _p, _l, _p, _p, _p, _l, _l, _i, _i, _p], c_int),
     "ub200_rope_qk": ([_p, _l, _l, _l, _p, _l, _l, _l, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i,
                        _i, _i, _i, _p], c_int),
     "ub200_glu_fwd": ([_i, _p, _p, _p, _l, _i, _p], c_int),

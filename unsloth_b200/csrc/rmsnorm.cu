@@ -273,6 +273,141 @@ __global__ void __launch_bounds__(256) rms_bwd_packed_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Residual add fused with the NEXT RMSNorm (Llama / Mistral decoder layers):
+//   S = A + B (one bf16 rounding, exactly torch's bf16 add) ; Y = RMSNorm(S) ; r = rsqrt(...)
+// and, for the backward, the norm gradient accumulated straight into the residual-stream gradient:
+//   dS += rms_bwd(dY, S, W, r)
+// The reference does these as separate passes (models/llama.py:838-844: `residual + hidden_states`
+// then fast_rms_layernorm); fusing removes one full read+write of the residual stream per norm
+// in each direction (4 instead of 5 / 6 tensor passes).  16-bit activations, same-dtype weights.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VPT>
+__global__ void __launch_bounds__(256) add_rms_fwd_packed_kernel(
+    const T* __restrict__ A, int64_t as, const T* __restrict__ B, int64_t bs,
+    const T* __restrict__ W, T* __restrict__ S, int64_t ss_, T* __restrict__ Y, int64_t ys,
+    float* __restrict__ r, int64_t n_rows, int n_cols, float eps) {
+  using T2 = typename Pk<T>::T2;
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  union V16 { int4 q; T2 h[4]; };
+  V16 w[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int c = (j * blockDim.x + tid) * 8;
+    w[j].q = (c < n_cols) ? *reinterpret_cast<const int4*>(W + c) : make_int4(0, 0, 0, 0);
+  }
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const T* a = A + row * as;
+    const T* b = B + row * bs;
+    V16 xs[VPT];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int c = (j * blockDim.x + tid) * 8;
+      if (c < n_cols) {
+        V16 va, vb;
+        va.q = __ldcs(reinterpret_cast<const int4*>(a + c));
+        vb.q = __ldcs(reinterpret_cast<const int4*>(b + c));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xs[j].h[i] = __hadd2(va.h[i], vb.h[i]);
+        *reinterpret_cast<int4*>(S + row * ss_ + c) = xs[j].q;
+      } else {
+        xs[j].q = make_int4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = Pk<T>::up(xs[j].h[i]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+    ss = block_sum(ss, red);
+    const float inv = rsqrtf(ss / (float)n_cols + eps);
+    if (tid == 0) r[row] = inv;
+    T* y = Y + row * ys;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int c = (j * blockDim.x + tid) * 8;
+      if (c < n_cols) {
+        V16 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = Pk<T>::up(xs[j].h[i]);
+          o.h[i] = __hmul2(Pk<T>::down(f.x * inv, f.y * inv), w[j].h[i]);
+        }
+        *reinterpret_cast<int4*>(y + c) = o.q;
+      }
+    }
+  }
+}
+
+template <typename T, int VPT>
+__global__ void __launch_bounds__(256) rms_bwd_acc_packed_kernel(
+    const T* __restrict__ dY, int64_t dys, const T* __restrict__ X, int64_t xs,
+    const T* __restrict__ W, const float* __restrict__ r, T* dS, int64_t dss, int64_t n_rows,
+    int n_cols) {
+  using T2 = typename Pk<T>::T2;
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  union V16 { int4 q; T2 h[4]; };
+  V16 w[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int c = (j * blockDim.x + tid) * 8;
+    w[j].q = (c < n_cols) ? *reinterpret_cast<const int4*>(W + c) : make_int4(0, 0, 0, 0);
+  }
+  const float n = (float)n_cols;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const T* dy = dY + row * dys;
+    const T* x = X + row * xs;
+    T* ds = dS + row * dss;
+    V16 a[VPT], b[VPT], g[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int c = (j * blockDim.x + tid) * 8;
+      if (c < n_cols) {
+        a[j].q = __ldcs(reinterpret_cast<const int4*>(dy + c));
+        b[j].q = __ldcs(reinterpret_cast<const int4*>(x + c));
+        g[j].q = *reinterpret_cast<const int4*>(ds + c);
+      } else {
+        a[j].q = b[j].q = g[j].q = make_int4(0, 0, 0, 0);
+      }
+    }
+    const float inv = r[row];
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 fy = Pk<T>::up(a[j].h[i]), fx = Pk<T>::up(b[j].h[i]), fw = Pk<T>::up(w[j].h[i]);
+        acc = fmaf(fy.x * fw.x, fx.x * inv, acc);
+        acc = fmaf(fy.y * fw.y, fx.y * inv, acc);
+      }
+    }
+    acc = block_sum(acc, red);
+    const float k = inv / n;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int c = (j * blockDim.x + tid) * 8;
+      if (c < n_cols) {
+        V16 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 fy = Pk<T>::up(a[j].h[i]), fx = Pk<T>::up(b[j].h[i]), fw = Pk<T>::up(w[j].h[i]);
+          const float2 fg = Pk<T>::up(g[j].h[i]);
+          o.h[i] = Pk<T>::down(fg.x + k * (n * (fy.x * fw.x) - (fx.x * inv) * acc),
+                               fg.y + k * (n * (fy.y * fw.y) - (fx.y * inv) * acc));
+        }
+        *reinterpret_cast<int4*>(ds + c) = o.q;
+      }
+    }
+  }
+}
+
 template <typename T, bool GEMMA, typename F>
 static int dispatch_vpt(int n_cols, F&& launch) {
   constexpr int V = DT<T>::VEC;
@@ -394,6 +529,70 @@ extern "C" int ub200_rms_layernorm_bwd(const void* dY, int64_t dy_row_stride, co
   else if (dtype == UB200_F16) { GO(__half); }
   else if (dtype == UB200_F32) { GO(float); }
   else return UB200_ERR_BAD_ARG;
+#undef GO
+  if (rc) return rc;
+  UB_RETURN_LAST();
+}
+
+extern "C" int ub200_add_rms_layernorm_fwd(const void* A, int64_t a_row_stride, const void* B,
+                                           int64_t b_row_stride, const void* W, void* S,
+                                           int64_t s_row_stride, void* Y, int64_t y_row_stride,
+                                           float* r, int64_t n_rows, int n_cols, float eps, int dtype,
+                                           cudaStream_t stream) {
+  using namespace ub;
+  if (n_rows <= 0) return UB200_OK;
+  if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_UNSUPPORTED;
+  if (n_cols % 8 || a_row_stride % 8 || b_row_stride % 8 || s_row_stride % 8 || y_row_stride % 8)
+    return UB200_ERR_BAD_ARG;
+  if (!aligned16(A) || !aligned16(B) || !aligned16(W) || !aligned16(S) || !aligned16(Y)) return UB200_ERR_BAD_ARG;
+  int rc;
+#define GO(T)                                                                                        \
+  rc = dispatch_vpt<T, false>(n_cols, [&](auto vpt, int threads) {                                   \
+    static int occ = 0;                                                                              \
+    if (!occ) {                                                                                      \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                                 \
+          &occ, add_rms_fwd_packed_kernel<T, decltype(vpt)::value>, threads, 0);                     \
+      if (occ < 1) occ = 1;                                                                          \
+    }                                                                                                \
+    const int64_t cap = (int64_t)UB_SM_COUNT * occ;                                                  \
+    add_rms_fwd_packed_kernel<T, decltype(vpt)::value>                                               \
+        <<<(int)(n_rows < cap ? n_rows : cap), threads, 0, stream>>>(                                \
+            (const T*)A, a_row_stride, (const T*)B, b_row_stride, (const T*)W, (T*)S, s_row_stride,  \
+            (T*)Y, y_row_stride, r, n_rows, n_cols, eps);                                            \
+    return UB200_OK;                                                                                 \
+  })
+  if (dtype == UB200_BF16) { GO(__nv_bfloat16); } else { GO(__half); }
+#undef GO
+  if (rc) return rc;
+  UB_RETURN_LAST();
+}
+
+extern "C" int ub200_rms_layernorm_bwd_acc(const void* dY, int64_t dy_row_stride, const void* X,
+                                           int64_t x_row_stride, const void* W, const float* r,
+                                           void* dS, int64_t ds_row_stride, int64_t n_rows,
+                                           int n_cols, int dtype, cudaStream_t stream) {
+  using namespace ub;
+  if (n_rows <= 0) return UB200_OK;
+  if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_UNSUPPORTED;
+  if (n_cols % 8 || dy_row_stride % 8 || x_row_stride % 8 || ds_row_stride % 8) return UB200_ERR_BAD_ARG;
+  if (!aligned16(dY) || !aligned16(X) || !aligned16(W) || !aligned16(dS)) return UB200_ERR_BAD_ARG;
+  int rc;
+#define GO(T)                                                                                        \
+  rc = dispatch_vpt<T, false>(n_cols, [&](auto vpt, int threads) {                                   \
+    static int occ = 0;                                                                              \
+    if (!occ) {                                                                                      \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                                 \
+          &occ, rms_bwd_acc_packed_kernel<T, decltype(vpt)::value>, threads, 0);                     \
+      if (occ < 1) occ = 1;                                                                          \
+    }                                                                                                \
+    const int64_t cap = (int64_t)UB_SM_COUNT * occ;                                                  \
+    rms_bwd_acc_packed_kernel<T, decltype(vpt)::value>                                               \
+        <<<(int)(n_rows < cap ? n_rows : cap), threads, 0, stream>>>(                                \
+            (const T*)dY, dy_row_stride, (const T*)X, x_row_stride, (const T*)W, r, (T*)dS,          \
+            ds_row_stride, n_rows, n_cols);                                                          \
+    return UB200_OK;                                                                                 \
+  })
+  if (dtype == UB200_BF16) { GO(__nv_bfloat16); } else { GO(__half); }
 #undef GO
   if (rc) return rc;
   UB_RETURN_LAST();

@@ -2,7 +2,7 @@
 from .cross_entropy_loss import (fast_cross_entropy_loss, Fast_CrossEntropyLoss,
                                  unsloth_fused_ce_loss, MAX_FUSED_SIZE)
 from .rms_layernorm import (fast_rms_layernorm, Fast_RMS_Layernorm, patch_rms_layernorm,
-                            unpatch_rms_layernorm)
+                            unpatch_rms_layernorm, fast_add_rms_layernorm, Fast_Add_RMS_Layernorm)
 from .rope_embedding import fast_rope_embedding, Fast_RoPE_Embedding, Fast_RoPE_Embedding_QK
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
 from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,

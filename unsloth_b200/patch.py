@@ -29,7 +29,7 @@ import torch
 from . import kernels as K
 from .lora import LoraLinear
 from .nf4 import Linear4bit
-from .packing import mask_packed_boundary_labels
+from .packing import get_packed_info_from_kwargs, mask_packed_boundary_labels, packed_position_ids
 
 # model shapes of BASELINE.json configs (public model cards)
 CONFIGS = {
@@ -98,12 +98,24 @@ class RotaryCache:
 _SDPA_CUDNN = {"ok": None}
 
 
-def _attention(Q, K_, V, scale, window, softcap):
+def _attention(Q, K_, V, scale, window, softcap, seq_info=None):
     """External library call, like the reference's dispatcher (utils/attention_dispatch.py:298-617:
     flash-attn | xformers | SDPA), on [B, S, H, D] views of the projection buffers (GQA native,
     no copies).  Plain causal attention goes to torch SDPA's cuDNN backend (Blackwell-native fused
     attention, ~3x flash-attn 2 on B200, benchmarks/attn_bench.py); sliding window / soft-capping
-    (Mistral, Gemma-2) go to flash-attn 2, which supports them."""
+    (Mistral, Gemma-2) go to flash-attn 2, which supports them.  Packed rows (`seq_info` =
+    (lengths, cu_seqlens, max_seqlen), packing.py:586-606) take flash-attn's varlen entry with the
+    reference's arguments (attention_dispatch.py:433-447): block-diagonal causal, no copies."""
+    if seq_info is not None:
+        from flash_attn import flash_attn_varlen_func
+        bsz, q_len, n_heads, hd = Q.shape
+        _, cu, max_len = seq_info
+        o = flash_attn_varlen_func(Q.reshape(bsz * q_len, n_heads, hd),
+                                   K_.reshape(bsz * q_len, K_.shape[2], hd),
+                                   V.reshape(bsz * q_len, V.shape[2], hd), cu, cu, max_len, max_len,
+                                   dropout_p=0.0, softmax_scale=scale, causal=True,
+                                   window_size=window, softcap=softcap)
+        return o.view(bsz, q_len, n_heads, hd)
     if window == (-1, -1) and not softcap and _SDPA_CUDNN["ok"] is not False:
         import torch.nn.functional as F
         from torch.nn.attention import SDPBackend, sdpa_kernel
@@ -122,7 +134,10 @@ def _attention(Q, K_, V, scale, window, softcap):
                            window_size=window, softcap=softcap)
 
 
-def LlamaAttention_fast_forward(self, hidden_states, cos, sin, position_ids=None):
+FUSE_ADD_NORM = True      # tests flip this to compare against the layer-by-layer form
+
+
+def LlamaAttention_fast_forward(self, hidden_states, cos, sin, position_ids=None, seq_info=None):
     """models/llama.py:671-771 (training branch), mistral.py:61-157, gemma2.py:86-201."""
     bsz, q_len, _ = hidden_states.size()
     n_heads, n_kv, hd = self._ub_heads
@@ -132,19 +147,20 @@ def LlamaAttention_fast_forward(self, hidden_states, cos, sin, position_ids=None
     Q, Kt = K.fast_rope_embedding(Q, Kt, cos, sin, position_ids)        # llama.py:730, in place
     window = (-1, -1)
     sw = self._ub_window
-    if sw is not None and q_len > sw:                                   # mistral.py:112-120
+    longest = q_len if seq_info is None else seq_info[2]
+    if sw is not None and longest > sw:                                 # mistral.py:112-120
         window = (sw, sw)
     A = _attention(Q.transpose(1, 2), Kt.transpose(1, 2), V.view(bsz, q_len, n_kv, hd),
-                   self._ub_scale, window, self._ub_softcap)
+                   self._ub_scale, window, self._ub_softcap, seq_info)
     return self.apply_o(self, A.reshape(bsz, q_len, n_heads * hd))      # llama.py:768
 
 
-def DecoderLayer_fast_forward(self, hidden_states, cos, sin, position_ids=None):
+def DecoderLayer_fast_forward(self, hidden_states, cos, sin, position_ids=None, seq_info=None):
     """models/llama.py:823-844 (Llama / Mistral) and gemma2.py:258-283 (four norms)."""
     gemma = self._ub_gemma
     residual = hidden_states
     h = K.fast_rms_layernorm(self.input_layernorm, hidden_states, gemma=gemma)
-    h = LlamaAttention_fast_forward(self.self_attn, h, cos, sin, position_ids)
+    h = LlamaAttention_fast_forward(self.self_attn, h, cos, sin, position_ids, seq_info)
     if gemma:
         h = K.fast_rms_layernorm(self.post_attention_layernorm, h, gemma=True)
     hidden_states = residual + h
@@ -159,7 +175,7 @@ def DecoderLayer_fast_forward(self, hidden_states, cos, sin, position_ids=None):
     return residual + h
 
 
-def Model_fast_forward(self, input_ids, position_ids=None):
+def Model_fast_forward(self, input_ids, position_ids=None, packed_seq_lengths=None):
     """models/llama.py:866-1230: embed, (Gemma: * sqrt(H) in model dtype :961-989), layers, norm."""
     h = self.embed_tokens(input_ids)
     if self._ub_gemma and not hasattr(self.embed_tokens, "embed_scale"):
@@ -169,19 +185,40 @@ def Model_fast_forward(self, input_ids, position_ids=None):
     seq_len = input_ids.shape[1]
     need = seq_len
     cos, sin = self._ub_rotary.get(need)
+    # packed / padding-free rows (llama.py:706, :721-723): per-document attention through
+    # cu_seqlens and RoPE through the reset-style position ids (derived when the collator
+    # did not send them)
+    seq_info = get_packed_info_from_kwargs({"packed_seq_lengths": packed_seq_lengths}, h.device,
+                                           input_ids.numel())
+    if seq_info is not None and position_ids is None:
+        position_ids = packed_position_ids(packed_seq_lengths, input_ids.numel(), h.device)
     idx = None
     if position_ids is not None:
         idx = position_ids.reshape(-1).to(torch.int32)
-    for layer in self.layers:
-        h = DecoderLayer_fast_forward(layer, h, cos, sin, idx)
-    return K.fast_rms_layernorm(self.norm, h, gemma=self._ub_gemma)
+    if self._ub_gemma or not FUSE_ADD_NORM:
+        for layer in self.layers:
+            h = DecoderLayer_fast_forward(layer, h, cos, sin, idx, seq_info)
+        return K.fast_rms_layernorm(self.norm, h, gemma=self._ub_gemma)
+    # Llama / Mistral: every `residual + branch` is fused with the norm that consumes the sum
+    # (this layer's post_attention_layernorm, then the NEXT layer's input_layernorm or the final
+    # norm), so the residual stream is read and written once per norm instead of twice.
+    layers = list(self.layers)
+    residual = h
+    normed = K.fast_rms_layernorm(layers[0].input_layernorm, h)
+    for i, layer in enumerate(layers):
+        a = LlamaAttention_fast_forward(layer.self_attn, normed, cos, sin, idx, seq_info)
+        residual, normed = K.fast_add_rms_layernorm(layer.post_attention_layernorm, residual, a)
+        m = layer.mlp(normed)
+        nxt = layers[i + 1].input_layernorm if i + 1 < len(layers) else self.norm
+        residual, normed = K.fast_add_rms_layernorm(nxt, residual, m)
+    return normed
 
 
 def CausalLM_fast_forward(self, input_ids=None, labels=None, position_ids=None,
                           packed_seq_lengths=None, num_items_in_batch=None, **kwargs):
     """models/llama.py:1371-1590, the `labels is not None and not UNSLOTH_RETURN_LOGITS` branch:
     boundary-mask packed labels (:1483), logits-free fused CE (:1497-1509), EMPTY logits."""
-    hidden = Model_fast_forward(self.model, input_ids, position_ids)
+    hidden = Model_fast_forward(self.model, input_ids, position_ids, packed_seq_lengths)
     if labels is None:
         return SimpleNamespace(loss=None, logits=None, hidden_states=hidden)
     labels = mask_packed_boundary_labels(labels, packed_seq_lengths)
