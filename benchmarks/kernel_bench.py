@@ -91,6 +91,34 @@ def main():
         f = lambda: L.call("ub200_glu_bwd", 0, L.ptr(DW), L.ptr(e), L.ptr(g), e.numel(), L.BF16, L.stream())
         report("swiglu_bwd", timeit(f), bytes_=6 * T * I * 2)
         del e, g, h, DW
+    if "addrms" in only or not only:
+        A = torch.randn(T, H, device=DEV, dtype=BF); B = torch.randn(T, H, device=DEV, dtype=BF)
+        S = torch.empty_like(A); Y = torch.empty_like(A); r = torch.empty(T, device=DEV)
+        W = N.weight
+        f = lambda: L.call("ub200_add_rms_layernorm_fwd", L.ptr(A), H, L.ptr(B), H, L.ptr(W), L.ptr(S), H,
+                           L.ptr(Y), H, L.ptr(r), T, H, 1e-5, L.BF16, L.stream())
+        report("add_rms_fwd", timeit(f), bytes_=4 * T * H * 2 + 4 * T)
+        f = lambda: L.call("ub200_rms_layernorm_bwd_acc", L.ptr(A), H, L.ptr(S), H, L.ptr(W), L.ptr(r),
+                           L.ptr(B), H, T, H, L.BF16, L.stream())
+        report("rms_bwd_acc", timeit(f), bytes_=4 * T * H * 2)
+        del A, B, S, Y
+    if "gemv" in only or not only:
+        for (m, k) in ((H, H), (I, H), (H, I)):
+            Wd = (torch.randn(m, k, device=DEV) * 0.02).to(BF)
+            packed, qs = quantize_nf4(Wd)
+            x = torch.randn(1, 1, k, device=DEV, dtype=BF)
+            out = torch.empty(1, 1, m, device=DEV, dtype=BF)
+            f = lambda: K.fast_gemv(x, packed, qs, out=out)
+            n = m * k
+            report("gemv_nf4_%dx%d" % (m, k), timeit(f, iters=20), bytes_=n * (0.5 + 1 / 64) + 2 * (m + k))
+            del Wd
+        lm = torch.randn(V, H, device=DEV, dtype=BF); x = torch.randn(H, device=DEV, dtype=BF)
+        o = torch.empty(V, device=DEV, dtype=BF)
+        f = lambda: L.call("ub200_gemv_dense", L.ptr(x), L.ptr(lm), H, L.ptr(o), V, H, L.BF16, L.BF16, L.stream())
+        report("gemv_dense_lm_head", timeit(f, iters=20), bytes_=V * H * 2 + 2 * (V + H))
+        f = lambda: torch.mv(lm, x, out=o)
+        report("torch_mv_lm_head", timeit(f, iters=20), bytes_=V * H * 2 + 2 * (V + H))
+        del lm
     if "nf4" in only or not only:
         Wd = (torch.randn(I, H, device=DEV) * 0.02).to(BF)
         packed, qs = quantize_nf4(Wd)

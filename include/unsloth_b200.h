@@ -135,6 +135,42 @@ void cdequantize_blockwise_fp16_nf4(float* code, unsigned char* A, float* absmax
                                     int blocksize, const int n, cudaStream_t stream);
 #endif
 
+/* ---- decode-time GEMV ---------------------------------------------------------
+ * out[m] = W[m,k] . x[k] with W NF4-packed, expanded in registers: the launch behind `fast_gemv`
+ * (unsloth/kernels/utils.py:874-973) and the q_len == 1 branch of `fast_linear_forward`
+ * (:1082-1125).  absmax either ready in fp32 (absmax_f32 != NULL, the bitsandbytes contract) or
+ * rebuilt in-kernel from the double-quantised statistics (absmax_q, code2, absmax2, offset):
+ * this folds the reference's cdequantize_blockwise_fp32 launch and `+= offset` (:938-948).
+ * code16: the 16-entry NF4 table (`quant_state.code`), NULL = built-in.  Optional LoRA epilogue
+ * out[row] += s * lora_B[row,:r] . lora_t[:r] (lora_t = A x in fp32; :1108-1112).
+ * x, out, lora_B in `dtype` (BF16 / F16); k % 32 == 0, blocksize % 32 == 0.                     */
+int ub200_gemv_nf4(const void* x, const uint8_t* packed, const float* absmax_f32,
+                   const uint8_t* absmax_q, const float* code2, const float* absmax2,
+                   const float* offset, const float* code16, void* out, int m, int k,
+                   int blocksize, int blocksize2, const void* lora_B, int ldb, const float* lora_t,
+                   int r, float s, int dtype, cudaStream_t stream);
+/* 16-bit dense rows: out[m] = W[m,k] . x[k] (`torch.mv(lm_head, h)`, models/llama.py:1460; the
+ * LoRA temp A x).  out_dtype F32 or `dtype`.                                                    */
+int ub200_gemv_dense(const void* x, const void* W, int64_t ldw, void* out, int m, int k, int dtype,
+                     int out_dtype, cudaStream_t stream);
+/* bitsandbytes symbols bound at unsloth/kernels/utils.py:283-284 (call :955-973): A = x[k],
+ * B = packed [m, k/2], absmax fp32, datatype = 16-entry code, n == 1; void return.              */
+#ifdef __CUDACC__
+void cgemm_4bit_inference_naive_bf16(int m, int n, int k, __nv_bfloat16* A, unsigned char* B,
+                                     float* absmax, float* datatype, __nv_bfloat16* out, int lda,
+                                     int ldb, int ldc, int blocksize, cudaStream_t stream);
+void cgemm_4bit_inference_naive_fp16(int m, int n, int k, __half* A, unsigned char* B,
+                                     float* absmax, float* datatype, __half* out, int lda, int ldb,
+                                     int ldc, int blocksize, cudaStream_t stream);
+#else
+void cgemm_4bit_inference_naive_bf16(int m, int n, int k, void* A, unsigned char* B, float* absmax,
+                                     float* datatype, void* out, int lda, int ldb, int ldc,
+                                     int blocksize, cudaStream_t stream);
+void cgemm_4bit_inference_naive_fp16(int m, int n, int k, void* A, unsigned char* B, float* absmax,
+                                     float* datatype, void* out, int lda, int ldb, int ldc,
+                                     int blocksize, cudaStream_t stream);
+#endif
+
 /* ---- tcgen05 GEMM ---------------------------------------------------------------------------
  * The primitive under matmul_lora (unsloth/kernels/utils.py:1128-1170) and the dX / dA / dB
  * GEMMs of LoRA_MLP / LoRA_QKV / LoRA_W.backward (unsloth/kernels/fast_lora.py:116-229,

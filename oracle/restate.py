@@ -384,6 +384,28 @@ def fast_dequantize(W, quant_state=None):
     return out.t() if W.shape[0] == 1 else out
 
 
+def gemv_nf4(x, packed, qs):
+    """`fast_gemv`, kernels/utils.py:874-973 (bsz == q_len == 1): fp32 absmax (:938-948), then
+    bitsandbytes' 4-bit GEMV out[m] = sum_k NF4[nibble(m,k)] * absmax[(m*K+k)//bs] * x[k], rounded
+    once to quant_state.dtype.  bitsandbytes is absent (parity unpinned): this is the exact-product
+    fp32 form; the original multiplies in the 16-bit dtype before accumulating in fp32."""
+    absmax = dequantize_absmax(qs)
+    b = packed.reshape(-1).long()
+    idx = torch.stack([b >> 4, b & 0xF], dim=1).reshape(-1)
+    Wf = (NF4_CODE[idx] * absmax[torch.arange(idx.numel()) // qs.blocksize]).reshape(qs.shape)
+    return (Wf.double() @ x.reshape(-1).double()).float().to(qs.dtype)
+
+
+def fast_linear_forward(x, packed, qs, A, B, s):
+    """kernels/utils.py:1082-1125, bsz == q_len == 1: out = gemv(x) ; temp = A x ; out += s B temp
+    (adapters cast to the activation dtype, :1103-1105; fp32 accumulation, one final rounding)."""
+    base = gemv_nf4(x, packed, qs).float() if qs is not None else (packed.float() @ x.reshape(-1).float())
+    if A is None:
+        return base.to(x.dtype)
+    t = A.to(x.dtype).float() @ x.reshape(-1).float()
+    return (base + s * (B.to(x.dtype).float() @ t)).to(x.dtype)
+
+
 # --------------------------------------------------------------------------------------
 # LoRA projections  (kernels/utils.py matmul_lora, kernels/fast_lora.py)
 # --------------------------------------------------------------------------------------

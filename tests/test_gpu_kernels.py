@@ -327,6 +327,91 @@ def test_nf4_dequant_bit_exact_and_bnb_symbols():
     assert torch.equal(out3, fast_dequantize(packed, qs16))
 
 
+@pytest.mark.parametrize("m,k,dt", [(4096, 4096, torch.bfloat16), (14336, 4096, torch.bfloat16),
+                                    (1000, 1024, torch.float16), (4096, 14336, torch.bfloat16)])
+def test_fast_gemv_nf4_vs_oracle_and_bnb_symbol(m, k, dt):
+    """Decode-time GEMV on the packed weight: against the oracle's exact-product
+    restatement, against dequantise-then-matmul on the GPU, and through the bitsandbytes symbol
+    with the argument list of kernels/utils.py:955-973."""
+    from unsloth_b200 import _lib as L
+    from unsloth_b200.kernels import fast_dequantize, fast_gemv
+    from unsloth_b200.nf4 import quantize_nf4
+    torch.manual_seed(m + k)
+    W = (torch.randn(m, k) * 0.02).to(dt).to(DEV)
+    packed, qs = quantize_nf4(W)
+    x = torch.randn(1, 1, k).to(dt).to(DEV)
+    out = fast_gemv(x, packed, qs)
+    assert out.shape == (1, 1, m) and out.dtype == dt
+    from types import SimpleNamespace as NS
+    qs_cpu = NS(absmax=qs.absmax.cpu(), shape=qs.shape, dtype=dt, blocksize=64, offset=qs.offset.cpu(),
+                state2=NS(absmax=qs.state2.absmax.cpu(), code=qs.state2.code.cpu(), blocksize=256))
+    ref = R.gemv_nf4(x.cpu(), packed.cpu(), qs_cpu)
+    # one rounding of an fp32 dot product on both sides: at most one ulp of the output dtype apart
+    o, rf = out.view(-1).float().cpu(), ref.float()
+    assert (o - rf).abs().max() <= 8e-3 * rf.abs().max()
+    assert ((o - rf).abs() > 1e-3 * rf.abs().max()).float().mean() < 0.02
+    Wd = fast_dequantize(packed, qs)
+    ref2 = (Wd.float() @ x.view(-1).float())
+    assert (out.view(-1).float() - ref2).abs().max() <= 1.2e-2 * ref2.abs().max()
+    # the bitsandbytes route: fp32 absmax first (cdequantize_blockwise_fp32 + offset), then the GEMV
+    absmax = torch.empty(qs.absmax.numel(), dtype=torch.float32, device=DEV)
+    L.lib.cdequantize_blockwise_fp32(L.ptr(qs.state2.code), L.ptr(qs.absmax), L.ptr(qs.state2.absmax),
+                                       L.ptr(absmax), 256, absmax.numel(), L.stream())
+    absmax += qs.offset
+    code = torch.tensor(R.NF4_CODE.tolist(), dtype=torch.float32, device=DEV)
+    out2 = torch.empty((1, 1, m), dtype=dt, device=DEV)
+    fx = L.lib.cgemm_4bit_inference_naive_bf16 if dt == torch.bfloat16 else L.lib.cgemm_4bit_inference_naive_fp16
+    fx(m, 1, k, L.ptr(x), L.ptr(packed), L.ptr(absmax), L.ptr(code), L.ptr(out2), m, (k + 1) // 2, m, 64,
+       L.stream())
+    assert (out2.float() - out.float()).abs().max() <= 8e-3 * out.float().abs().max()
+
+
+def test_fast_linear_forward_decode_and_merge_lora():
+    """fast_linear_forward (kernels/utils.py:1082-1125) at bsz == q_len == 1 with LoRA in the GEMV
+    epilogue, at bsz > 1 through the GEMM, on a dense weight, and `merge_lora` (save.py:620-646):
+    x @ merged.T must equal the unmerged projection."""
+    from unsloth_b200.kernels import fast_linear_forward, get_lora_parameters, fast_dequantize
+    from unsloth_b200.lora import LoraLinear
+    from unsloth_b200.nf4 import Linear4bit
+    from unsloth_b200.save import merge_lora
+    torch.manual_seed(21)
+    k, m = 2048, 3072
+    W = (torch.randn(m, k) * 0.02).to(torch.bfloat16).to(DEV)
+    proj = LoraLinear(Linear4bit.from_dense(W), r=16, lora_alpha=32, init_b_std=0.05)
+    Wq, qs, A, B, s = get_lora_parameters(proj)
+    Wd = fast_dequantize(Wq, qs).float()
+    full = Wd + s * (B.float() @ A.float())
+    x1 = torch.randn(1, 1, k, device=DEV).to(torch.bfloat16)
+    y1 = fast_linear_forward(proj, x1)
+    assert y1.shape == (1, 1, m)
+    ref1 = x1.view(-1).float() @ full.t()
+    assert (y1.view(-1).float() - ref1).abs().max() <= 1.2e-2 * ref1.abs().max()
+    from types import SimpleNamespace as NS
+    qs_cpu = NS(absmax=qs.absmax.cpu(), shape=qs.shape, dtype=torch.bfloat16, blocksize=64,
+                offset=qs.offset.cpu(),
+                state2=NS(absmax=qs.state2.absmax.cpu(), code=qs.state2.code.cpu(), blocksize=256))
+    ref_o = R.fast_linear_forward(x1.cpu(), Wq.cpu(), qs_cpu, A.detach().cpu(), B.detach().cpu(), s).float()
+    assert (y1.view(-1).float().cpu() - ref_o).abs().max() <= 8e-3 * ref_o.abs().max()
+    base_only = x1.view(-1).float() @ Wd.t()
+    assert (ref1 - base_only).abs().max() > 0.05 * ref1.abs().max()        # the LoRA term matters
+    x4 = torch.randn(4, 1, k, device=DEV).to(torch.bfloat16)
+    y4 = fast_linear_forward(proj, x4)
+    ref4 = x4.view(4, k).float() @ full.t()
+    assert y4.shape == (4, 1, m)
+    assert (y4.view(4, m).float() - ref4).abs().max() <= 1.5e-2 * ref4.abs().max()
+    # dense 16-bit base (LoRA without quantisation) and the lm_head-style GEMV
+    dense = LoraLinear(torch.nn.Linear(k, m, bias=False, device=DEV, dtype=torch.bfloat16), r=16,
+                       lora_alpha=32, init_b_std=0.05)
+    Wn, _, A2, B2, s2 = get_lora_parameters(dense)
+    yd = fast_linear_forward(dense, x1)
+    refd = x1.view(-1).float() @ (Wn.float() + s2 * (B2.float() @ A2.float())).t()
+    assert (yd.view(-1).float() - refd).abs().max() <= 1.2e-2 * refd.abs().max()
+    # merge: one rounding of W + sBA to bf16
+    Wm, bias = merge_lora(proj, "proj")
+    assert bias is None and Wm.dtype == torch.bfloat16 and Wm.shape == (m, k)
+    assert torch.equal(Wm, full.to(torch.bfloat16))
+
+
 def test_nf4_cfg2_size_properties():
     """A full Llama-3-8B gate_proj (14336 x 4096): quantise -> dequantise -> requantise is
     idempotent and the error is bounded by the NF4 grid."""

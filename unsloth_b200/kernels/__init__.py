@@ -10,4 +10,5 @@ from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
 from .fast_lora import (get_lora_parameters, get_lora_parameters_bias, apply_lora_mlp_swiglu,
                         apply_lora_mlp_geglu_exact, apply_lora_mlp_geglu_approx, apply_lora_qkv,
                         apply_lora_o, LoRA_MLP, LoRA_QKV, LoRA_W)
-from .utils import fast_dequantize, matmul_lora, QUANT_STATE, gemm
+from .utils import (fast_dequantize, matmul_lora, QUANT_STATE, gemm, fast_gemv,
+                    fast_linear_forward)

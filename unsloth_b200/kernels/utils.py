@@ -1,6 +1,7 @@
 """Host-side mirror of unsloth/kernels/utils.py for the hot path:
 `fast_dequantize` (:567-679), `matmul_lora` (:1128-1170), `get_lora_parameters[_bias]`
-(:335-440), `QUANT_STATE`, plus the thin `gemm` wrapper over ub200_gemm.
+(:335-440), `QUANT_STATE`, plus the thin `gemm` wrapper over ub200_gemm; and the decode-time
+consumers of the same NF4 format, `fast_gemv` (:874-973) and `fast_linear_forward` (:1082-1125).
 """
 from __future__ import annotations
 
@@ -69,6 +70,103 @@ def fast_dequantize(W, quant_state=None, out=None, use_global_buffer=False, _slo
            L.ptr(offset), L.ptr(out), numel, int(blocksize), int(blocksize2), L.dt(dtype), L.stream())
     is_transposed = True if W.shape[0] == 1 else False
     return out.t() if is_transposed else out
+
+
+# ---------------------------------------------------------------------------------------------
+# decode-time GEMV
+# ---------------------------------------------------------------------------------------------
+def _gemv_nf4(x, W, quant_state, out, lora_B=None, lora_t=None, s=0.0):
+    absmax, shape, dtype, blocksize, offset, absmax2, code2, blocksize2 = _unpack_quant_state(quant_state)
+    code16 = quant_state.code if type(quant_state) is not list else quant_state[6]
+    if not torch.is_tensor(offset):
+        offset = torch.tensor(float(offset), dtype=torch.float32, device=W.device)
+    if code16 is not None and (code16.dtype != torch.float32 or code16.numel() != 16):
+        raise RuntimeError("unsloth_b200: fast_gemv needs the 16-entry fp32 NF4 code")
+    if x.dtype != dtype or out.dtype != dtype:
+        raise RuntimeError("unsloth_b200: fast_gemv needs X and out in quant_state.dtype")
+    r = 0 if lora_B is None else lora_B.shape[1]
+    L.call("ub200_gemv_nf4", L.ptr(x), L.ptr(W), None, L.ptr(absmax), L.ptr(code2), L.ptr(absmax2),
+           L.ptr(offset), None if code16 is None else L.ptr(code16), L.ptr(out), int(shape[0]),
+           int(shape[1]), int(blocksize), int(blocksize2),
+           None if lora_B is None else L.ptr(lora_B), 0 if lora_B is None else lora_B.stride(0),
+           None if lora_t is None else L.ptr(lora_t), r, float(s), L.dt(dtype), L.stream())
+    return out
+
+
+@torch.inference_mode
+def fast_gemv(X, W, quant_state, out=None):
+    """kernels/utils.py:874-973: X [1, 1, in] against an NF4 weight -> [1, 1, out], the packed
+    weight expanded in registers.  ONE launch (the reference: a blockwise fp32 absmax launch, a
+    torch `+= offset`, then bitsandbytes' 4-bit GEMV)."""
+    if quant_state is None:
+        return torch.matmul(X, W, out=out)
+    L.require_cuda(X, W)
+    _, shape, dtype, *_ = _unpack_quant_state(quant_state)
+    if X.numel() != shape[1]:
+        raise RuntimeError("unsloth_b200: fast_gemv is the bsz == 1, q_len == 1 path")
+    if out is None:
+        out = torch.empty((1, 1, shape[0]), dtype=dtype, device=W.device)
+    _gemv_nf4(X.reshape(-1), W, quant_state, out)
+    return out
+
+
+def _fast_lora_cast(A, B, dtype):
+    """`lora_A._fast_lora` / `lora_B._fast_lora` (kernels/utils.py:1103-1105): adapters cast once to
+    the activation dtype for decoding (refreshed when the parameter is updated in place)."""
+    for p_ in (A, B):
+        c = getattr(p_, "_fast_lora", None)
+        if c is None or c.dtype != dtype or getattr(p_, "_fast_lora_version", None) != p_._version:
+            p_._fast_lora = p_.detach().to(dtype).contiguous()
+            p_._fast_lora_version = p_._version
+    return A._fast_lora, B._fast_lora
+
+
+@torch.inference_mode
+def fast_linear_forward(proj, X, temp_lora=None, out=None):
+    """kernels/utils.py:1082-1125: the decode-time projection.  q_len != 1 falls through to
+    matmul_lora; bsz == q_len == 1 on an NF4 weight is ONE GEMV launch with the LoRA term in its
+    epilogue (+ one 16-row GEMV for the LoRA temp A x); other shapes dequantise and use the GEMM."""
+    W, W_quant, lora_A, lora_B, lora_S, bias = get_lora_parameters_bias(proj)
+    bsz, q_len, in_dim = X.shape
+    if q_len != 1:
+        return matmul_lora(X, W, W_quant, lora_A, lora_B, lora_S)
+    L.require_cuda(X, W)
+    dtype = X.dtype
+    single = bsz == 1 and dtype in (torch.bfloat16, torch.float16) and in_dim % 32 == 0
+    if single and (W_quant is not None or W.dtype == dtype):
+        x = X.reshape(-1)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        out_dim = _unpack_quant_state(W_quant)[1][0] if W_quant is not None else W.shape[0]
+        if out is None:
+            out = torch.empty((1, 1, out_dim), dtype=dtype, device=X.device)
+        Bc = t = None
+        if lora_A is not None:
+            Ac, Bc = _fast_lora_cast(lora_A, lora_B, dtype)
+            t = temp_lora if temp_lora is not None and temp_lora.dtype == torch.float32 else \
+                torch.empty(Ac.shape[0], dtype=torch.float32, device=X.device)
+            L.call("ub200_gemv_dense", L.ptr(x), L.ptr(Ac), Ac.stride(0), L.ptr(t), Ac.shape[0],
+                   in_dim, L.dt(dtype), L.F32, L.stream())
+        if W_quant is not None:
+            _gemv_nf4(x, W, W_quant, out, Bc, t, lora_S or 0.0)
+        else:
+            Wc = W if W.stride(-1) == 1 else W.contiguous()
+            L.call("ub200_gemv_dense", L.ptr(x), L.ptr(Wc), Wc.stride(0), L.ptr(out), out_dim, in_dim,
+                   L.dt(dtype), L.dt(dtype), L.stream())
+            if lora_A is not None:
+                out.view(-1).addmv_(Bc, t.to(dtype), alpha=lora_S)
+        if bias is not None:
+            out += bias
+        return out
+    # bsz > 1 (or an odd shape): same arithmetic as the training primitive on [bsz, in] rows
+    out2 = matmul_lora(X.reshape(bsz, in_dim), W, W_quant, lora_A, lora_B, lora_S)
+    out2 = out2.view(bsz, 1, -1)
+    if bias is not None:
+        out2 = out2 + bias
+    if out is not None:
+        out.copy_(out2)
+        return out
+    return out2
 
 
 # ---------------------------------------------------------------------------------------------
