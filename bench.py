@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--rank", type=int, default=RANK_R)
     ap.add_argument("--sliding-window", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-keep-dequant", action="store_true",
+                    help="re-dequantise the NF4 weights in the backward (the reference's schedule) instead of "
+                         "keeping the forward's 16-bit expansion resident until the layer's backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-tokens", type=int, default=512)
     a = ap.parse_args()
@@ -242,6 +245,9 @@ def run_ours(args):
         extra["sliding_window"] = args.sliding_window
     if args.seq > 8192:
         extra["max_position_embeddings"] = args.seq
+    from unsloth_b200.kernels import utils as KU
+    if args.no_keep_dequant:
+        KU.set_keep_dequant(False)
     model = build_qlora_model(args.model, r=args.rank, lora_alpha=args.rank, device=dev, seed=3407,
                               num_hidden_layers=args.layers, **extra)
     bucket = FlatLoRABucket(lora_parameters(model), lr=2e-4, weight_decay=0.01)
@@ -378,6 +384,9 @@ def run_ours(args):
                        "layers": model.config.num_hidden_layers, "gradient_checkpointing": False,
                        "optimizer": "AdamW on the flat LoRA bucket (%d params)" % bucket.numel(),
                        "cuda_graph": graph_note,
+                       "keep_dequant": ("dequantised weights stay resident from a layer's forward to its backward "
+                                        "(+2 B per base parameter of peak memory)") if KU.keep_dequant()
+                                       else "off: weights re-dequantised in the backward",
                        "l2_policy": "inputs larger than L2 (each step streams > 5 GB of NF4 weights and activations)"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 2),
                     "h2d_bytes_per_step": 2 * args.bs * args.seq * 8, "d2h_bytes_per_step": 4},

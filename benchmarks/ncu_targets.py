@@ -1,5 +1,5 @@
 """ncu targets: `python benchmarks/ncu_targets.py <name>` launches a few instances of one kernel
-at cfg2 sizes (names: gemm2, skinny, dequant, rms, rope, ce)."""
+at cfg2 sizes (names: gemm2, skinny, dequant, rms, rope, ce, gemv)."""
 import os
 import sys
 
@@ -31,6 +31,13 @@ elif name == "dequant":
     p, q = quantize_nf4(W); out = torch.empty_like(W)
     for _ in range(4):
         K.fast_dequantize(p, q, out=out)
+elif name == "gemv":
+    from unsloth_b200.nf4 import quantize_nf4
+    W = (torch.randn(I, H, device=DEV) * 0.02).to(BF)
+    p, q = quantize_nf4(W)
+    x = torch.randn(1, 1, H, device=DEV, dtype=BF); out = torch.empty(1, 1, I, device=DEV, dtype=BF)
+    for _ in range(3):
+        K.fast_gemv(x, p, q, out=out)
 elif name == "rms":
     X = torch.randn(T, H, device=DEV, dtype=BF); W = torch.ones(H, device=DEV, dtype=BF)
     Y = torch.empty_like(X); r = torch.empty(T, device=DEV); dY = torch.randn(T, H, device=DEV, dtype=BF)

@@ -210,6 +210,37 @@ def test_training_reduces_loss_and_is_deterministic():
     assert max(abs(x - y) for x, y in zip(a, b)) < 2e-3, (a, b)
 
 
+def test_keep_dequant_policy_does_not_change_results():
+    """keep_dequant (the 16-bit expansion of a weight kept from a layer's forward to its backward) is
+    a pure memory-for-bandwidth trade: same loss, same LoRA gradients as re-dequantising."""
+    from unsloth_b200.kernels import utils as KU
+    from unsloth_b200.patch import build_qlora_model, lora_parameters
+    model = build_qlora_model("llama-3-8b", r=8, lora_alpha=16, device=DEV, num_hidden_layers=2,
+                              init_b_std=0.05, **TINY)
+    torch.manual_seed(3)
+    ids = torch.randint(0, TINY["vocab_size"], (2, 64), device=DEV)
+    res = {}
+    try:
+        for keep in (True, False):
+            KU.set_keep_dequant(keep)
+            KU.bump_param_epoch()                       # both passes redo the per-step LoRA casts
+            for p_ in lora_parameters(model):
+                p_.grad = None
+            n0 = __import__("unsloth_b200._lib", fromlist=["x"]).launch_count
+            loss = model(input_ids=ids, labels=ids).loss
+            loss.backward()
+            n1 = __import__("unsloth_b200._lib", fromlist=["x"]).launch_count
+            res[keep] = (loss.item(), torch.cat([p_.grad.flatten() for p_ in lora_parameters(model)]), n1 - n0)
+    finally:
+        KU.set_keep_dequant(None)
+    assert res[True][0] == res[False][0], (res[True][0], res[False][0])
+    a, b = res[True][1], res[False][1]
+    assert (a - b).abs().max() <= 1e-2 * b.abs().max()       # attention backward may not be bit-stable
+    # one dequant launch saved per projection and layer, except q/k/v of the first layer, whose dX
+    # (into the embedding output) is never formed
+    assert res[False][2] - res[True][2] == 2 * 7 - 3, (res[False][2], res[True][2])
+
+
 def test_cuda_graph_step_matches_eager():
     """GraphedTrainStep (fwd+bwd replayed from a CUDA graph) reproduces the eager step: same losses
     and same LoRA parameters after three optimiser steps (the per-step LoRA cast cache must be

@@ -30,7 +30,11 @@ __constant__ float kNF4g[16] = {
 template <typename T> struct P2;
 template <> struct P2<__nv_bfloat16> {
   using T2 = __nv_bfloat162;
-  __device__ static __forceinline__ float2 up(T2 v) { return __bfloat1622float2(v); }
+  // bf16 is the upper half of an fp32: one shift / one mask per element
+  __device__ static __forceinline__ float2 up(T2 v) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&v);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+  }
   __device__ static __forceinline__ __nv_bfloat16 down(float v) { return __float2bfloat16_rn(v); }
 };
 template <> struct P2<__half> {
@@ -39,86 +43,133 @@ template <> struct P2<__half> {
   __device__ static __forceinline__ __half down(float v) { return __float2half_rn(v); }
 };
 
+// THREADS = 128: small CTAs (8 rows) keep the last partial wave short; the 32 KB table limits an
+// SM to 7 of them, registers to 4-5.
+constexpr int GEMV_THREADS = 128;
+constexpr int GEMV_DEPTH = 4;      // 1024-column steps whose packed bytes are fetched together
+
 template <typename T, int ROWS>
-__global__ void __launch_bounds__(256) gemv_nf4_kernel(
+__global__ void __launch_bounds__(GEMV_THREADS) gemv_nf4_kernel(
     const T* __restrict__ x, const uint8_t* __restrict__ packed,
     const float* __restrict__ absmax_f32, const uint8_t* __restrict__ absmax_q,
     const float* __restrict__ code2, const float* __restrict__ absmax2,
     const float* __restrict__ offset, const float* __restrict__ code16, T* __restrict__ out, int m,
-    int k, int blocksize, int blocksize2, const T* __restrict__ lora_B, int ldb,
+    int k, int bs_shift, int bs2_shift, const T* __restrict__ lora_B, int ldb,
     const float* __restrict__ lora_t, int r, float s) {
   using T2 = typename P2<T>::T2;
   // byte -> (code[hi nibble], code[lo nibble]) in fp32, replicated 16x so that lane l always reads
   // copy l % 16: the 16 lanes of each 64-bit shared-memory wavefront hit 16 different bank pairs
   // whatever bytes they look up (an un-replicated table serialises ~7x on random nibbles).
-  __shared__ float2 lut2[256 * 16];
-  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
-    const int b = i >> 4;
-    const float hi = code16 ? code16[b >> 4] : kNF4g[b >> 4];
-    const float lo = code16 ? code16[b & 15] : kNF4g[b & 15];
-    lut2[i] = make_float2(hi, lo);
-  }
-  __syncthreads();
+  extern __shared__ __align__(16) unsigned char gemv_smem[];
+  float2* lut2 = reinterpret_cast<float2*>(gemv_smem);                 // 32 KB table
+  int4* xs = reinterpret_cast<int4*>(gemv_smem + 256 * 16 * sizeof(float2));   // x, k * 2 bytes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float2* lut = lut2 + (lane & 15);
+  const int row0 = (blockIdx.x * (GEMV_THREADS / 32) + warp) * ROWS;
+  const bool live = row0 < m;
   const float off = offset ? *offset : 0.f;
   const int64_t row_bytes = (int64_t)k / 2;
-  // persistent over row groups: the 32 KB table is built once per CTA
-  for (int row0 = (blockIdx.x * 8 + warp) * ROWS; row0 < m; row0 += gridDim.x * 8 * ROWS) {
-    float acc[ROWS];
+  // rows past the end alias the last row (their results are not stored)
+  const uint8_t* wrow[ROWS];
+  int64_t ebase[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
-    for (int c0 = lane * 32; c0 < k; c0 += 1024) {
-      union { int4 q; uint32_t u[4]; } w[ROWS];
+  for (int i = 0; i < ROWS; ++i) {
+    const int row = row0 + i < m ? row0 + i : m - 1;
+    wrow[i] = packed + row * row_bytes;
+    ebase[i] = (int64_t)row * k;
+  }
+  int4 w[GEMV_DEPTH][ROWS];
+  float am[GEMV_DEPTH][ROWS];
+  // all packed bytes and block scales of a 4096-column span are requested before anything is
+  // expanded: the first span's loads are in flight while the table is being built
+  auto fetch = [&](int cbase) {
 #pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const int row = row0 + i < m ? row0 + i : m - 1;
-        w[i].q = __ldcs(reinterpret_cast<const int4*>(packed + row * row_bytes + c0 / 2));
-      }
-      float xf[32];
+    for (int d = 0; d < GEMV_DEPTH; ++d) {
+      const int c0 = cbase + d * 1024 + lane * 32;
+      if (c0 < k) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        union { int4 v; T2 h[4]; } xv;
-        xv.v = __ldg(reinterpret_cast<const int4*>(x + c0) + q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = P2<T>::up(xv.h[j]);
-          xf[q * 8 + 2 * j] = f.x;
-          xf[q * 8 + 2 * j + 1] = f.y;
+        for (int i = 0; i < ROWS; ++i) {
+          w[d][i] = __ldcs(reinterpret_cast<const int4*>(wrow[i] + c0 / 2));
+          const int64_t blk = (ebase[i] + c0) >> bs_shift;        // block sizes are powers of two:
+          am[d][i] = absmax_f32 ? absmax_f32[blk]                 // no 64-bit divisions in the loop
+                                : fmaf(code2[absmax_q[blk]], absmax2[blk >> bs2_shift], off);
         }
-      }
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const int row = row0 + i < m ? row0 + i : m - 1;
-        const int64_t blk = ((int64_t)row * k + c0) / blocksize;
-        const float am = absmax_f32 ? absmax_f32[blk]
-                                    : fmaf(code2[absmax_q[blk]], absmax2[blk / blocksize2], off);
-        float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t byte = (w[i].u[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-          const float2 c = lut[byte * 16];
-          p0 = fmaf(c.x, xf[2 * j], p0);
-          p1 = fmaf(c.y, xf[2 * j + 1], p1);
-        }
-        acc[i] = fmaf(am, p0 + p1, acc[i]);
       }
     }
+  };
+  if (live) fetch(0);
+  for (int e = threadIdx.x; e < 256 * 16; e += GEMV_THREADS) {   // consecutive lanes, consecutive banks
+    const int b = e >> 4;
+    lut2[e] = make_float2(code16 ? code16[b >> 4] : kNF4g[b >> 4],
+                          code16 ? code16[b & 15] : kNF4g[b & 15]);
+  }
+  // x is staged once per CTA (every warp walks all of it).  16-byte chunk g = columns 8g..8g+7
+  // belongs to lane (g % 128) / 4, quarter g % 4 of 1024-column step g / 128; it is stored at
+  // step * 128 + quarter * 32 + lane so that the four 16-byte reads of a lane are conflict-free.
+  for (int g = threadIdx.x; g < k / 8; g += GEMV_THREADS) {
+    const int within = g & 127;
+    xs[(g & ~127) + (within & 3) * 32 + (within >> 2)] = __ldg(reinterpret_cast<const int4*>(x) + g);
+  }
+  __syncthreads();
+  if (!live) return;
+  // table address of byte b for this lane = b * 128 + (lane % 16) * 8: the byte is moved to bits
+  // 7..14 with one shift and merged with the lane bits by one 3-input logic op
+  const uint32_t lane_bits = (uint32_t)(lane & 15) << 3;
+  const char* lut_bytes = reinterpret_cast<const char*>(lut2);
+  float acc[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
+  for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
+#pragma unroll 1
+  for (int cbase = 0; cbase < k; cbase += GEMV_DEPTH * 1024) {
+    if (cbase) fetch(cbase);
 #pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const int row = row0 + i;
-        if (row < m) {
-          float v = acc[i];
-          if (lora_B) {
-            float d = 0.f;
-            for (int j = 0; j < r; ++j) d = fmaf(DT<T>::to_f(lora_B[(int64_t)row * ldb + j]), lora_t[j], d);
-            v = fmaf(s, d, v);
+    for (int d = 0; d < GEMV_DEPTH; ++d) {
+      const int c0 = cbase + d * 1024 + lane * 32;
+      if (c0 < k) {
+        float xf[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          union { int4 v; T2 h[4]; } xv;
+          xv.v = xs[(c0 >> 10) * 128 + q * 32 + lane];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = P2<T>::up(xv.h[j]);
+            xf[q * 8 + 2 * j] = f.x;
+            xf[q * 8 + 2 * j + 1] = f.y;
           }
-          out[row] = P2<T>::down(v);
         }
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          const uint32_t u[4] = {(uint32_t)w[d][i].x, (uint32_t)w[d][i].y, (uint32_t)w[d][i].z,
+                                 (uint32_t)w[d][i].w};
+          float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int sh = 8 * (j & 3) - 7;
+            const uint32_t word = u[j >> 2];
+            const uint32_t o = ((sh < 0 ? word << 7 : word >> sh) & 0x7F80u) | lane_bits;
+            const float2 c = *reinterpret_cast<const float2*>(lut_bytes + o);
+            p0 = fmaf(c.x, xf[2 * j], p0);
+            p1 = fmaf(c.y, xf[2 * j + 1], p1);
+          }
+          acc[i] = fmaf(am[d][i], p0 + p1, acc[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const int row = row0 + i;
+      if (row < m) {
+        float v = acc[i];
+        if (lora_B) {
+          float d = 0.f;
+          for (int j = 0; j < r; ++j) d = fmaf(DT<T>::to_f(lora_B[(int64_t)row * ldb + j]), lora_t[j], d);
+          v = fmaf(s, d, v);
+        }
+        out[row] = P2<T>::down(v);
       }
     }
   }
@@ -175,20 +226,22 @@ static int launch_gemv_nf4(const void* x, const uint8_t* packed, const float* ab
                            const float* offset, const float* code16, void* out, int m, int k,
                            int blocksize, int blocksize2, const void* lora_B, int ldb,
                            const float* lora_t, int r, float s, cudaStream_t st) {
-  // few rows: 2 per warp so that the grid still covers the SMs; many rows: 4 for more x reuse.
-  // At most two resident CTAs per SM (32 KB table each), each looping over its row groups.
-  const int cap = UB_SM_COUNT * 2;
-  if (m >= 8192) {
-    const int need = (m + 31) / 32;
-    gemv_nf4_kernel<T, 4><<<need < cap ? need : cap, 256, 0, st>>>(
-        (const T*)x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16, (T*)out, m, k,
-        blocksize, blocksize2, (const T*)lora_B, ldb, lora_t, r, s);
-  } else {
-    const int need = (m + 15) / 16;
-    gemv_nf4_kernel<T, 2><<<need < cap ? need : cap, 256, 0, st>>>(
-        (const T*)x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16, (T*)out, m, k,
-        blocksize, blocksize2, (const T*)lora_B, ldb, lora_t, r, s);
+  int bs_shift = 0, bs2_shift = 0;
+  while ((1 << bs_shift) < blocksize) ++bs_shift;
+  while ((1 << bs2_shift) < blocksize2) ++bs2_shift;
+  constexpr int ROWS = 2, RPC = ROWS * GEMV_THREADS / 32;          // rows per CTA
+  const size_t smem = 256 * 16 * sizeof(float2) + (size_t)((k + 1023) / 1024) * 1024 * sizeof(T);
+  if (smem > 220 * 1024) return UB200_ERR_UNSUPPORTED;
+  static size_t smem_set = 0;        // opt-in above 48 KB, raised monotonically (idempotent)
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_nf4_kernel<T, ROWS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
   }
+  gemv_nf4_kernel<T, ROWS><<<(m + RPC - 1) / RPC, GEMV_THREADS, smem, st>>>(
+      (const T*)x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16, (T*)out, m, k,
+      bs_shift, bs2_shift, (const T*)lora_B, ldb, lora_t, r, s);
   UB_RETURN_LAST();
 }
 
@@ -203,8 +256,9 @@ extern "C" int ub200_gemv_nf4(const void* x, const uint8_t* packed, const float*
   using namespace ub;
   if (m <= 0) return UB200_OK;
   if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_UNSUPPORTED;
-  if (k <= 0 || k % 32 || blocksize < 32 || blocksize % 32) return UB200_ERR_UNSUPPORTED;
+  if (k <= 0 || k % 32 || blocksize < 32 || (blocksize & (blocksize - 1))) return UB200_ERR_UNSUPPORTED;
   if (!absmax_f32 && (!absmax_q || !code2 || !absmax2 || blocksize2 <= 0)) return UB200_ERR_BAD_ARG;
+  if (!absmax_f32 && (blocksize2 & (blocksize2 - 1))) return UB200_ERR_UNSUPPORTED;
   if (lora_B && (!lora_t || r <= 0 || ldb < r)) return UB200_ERR_BAD_ARG;
   if (!x || !packed || !out || !al16(x) || !al16(packed)) return UB200_ERR_BAD_ARG;
   if (dtype == UB200_BF16)

@@ -21,6 +21,7 @@ import torch
 
 from .. import _lib as L
 from .utils import (RANK_BLOCK, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
+                    keep_dequant,
                     get_lora_parameters, get_lora_parameters_bias, matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
 from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
@@ -56,6 +57,7 @@ class _Group:
         self.T, self.in_f = X2.shape
         self.dtype = X2.dtype
         self.dev = X2.device
+        self.dense = None          # dequantised weights kept from forward to backward (keep_dequant)
         self._init_ranks()
 
     def drop_input(self):
@@ -104,16 +106,21 @@ class _Group:
             self._A_cat = A_cat
         return self._A_cat
 
-    def forward(self):
-        """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None."""
+    def forward(self, keep=False):
+        """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None.  `keep`: the
+        dequantised weights are private tensors left in `self.dense` for the backward."""
         X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
+        if keep:
+            self.dense = []
         XA = None
         if self.has_lora:
             XA = gemm(T, self.Rp, [(X2, self.A_cat(), self.in_f)],
                       torch.empty((T, self.Rp), dtype=dt, device=dev))
         outs = []
         for off, (W, Wq, A, B, s) in zip(self.offs, self.projs):
-            Wd = dense_weight(W, Wq, dt, 0)
+            Wd = dense_weight(W, Wq, dt, 0, fresh=keep)
+            if keep:
+                self.dense.append(Wd if Wq is not None else None)
             Bop, b_mn = as_b_operand(Wd)
             N = Wd.shape[0]
             segs = [(X2, Bop, self.in_f)]
@@ -168,8 +175,9 @@ class _Group:
             return None, grads
         # dX = sum_i dY_i @ W_i  +  G @ A_cat      (one launch; W_i as MN-major operands)
         segs = []
+        kept = self.dense if self.dense is not None else [None] * len(self.projs)
         for slot, (dY, (W, Wq, A, B, s)) in enumerate(zip(dYs, self.projs)):
-            Wd = dense_weight(W, Wq, dt, slot)          # logical [out, in]
+            Wd = kept[slot] if kept[slot] is not None else dense_weight(W, Wq, dt, slot)   # [out, in]
             # as the B operand of dY @ Wd we need [N=in, K=out]: that is Wd^T
             Bop, b_mn = as_b_operand(Wd.t())
             if not b_mn:
@@ -196,13 +204,15 @@ class LoRA_MLP(torch.autograd.Function):
         shape = X.shape
         X2 = _as2d(X)
         grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
-        (e, g), XA1 = grp.forward()
+        keep = keep_dequant() and any(ctx.needs_input_grad)
+        (e, g), XA1 = grp.forward(keep)
         b_s = shape[:-1]
         h = _forward_function(e.view(*b_s, -1) if X.dim() == 3 else e.view(1, *e.shape),
                               g.view(*b_s, -1) if X.dim() == 3 else g.view(1, *g.shape))
         h2 = h.reshape(-1, h.shape[-1])
         grp2 = _Group(h2, [(downW, downW_quant, downA, downB, downS)])
-        (i,), XA2 = grp2.forward()
+        (i,), XA2 = grp2.forward(keep)
+        ctx.dense = (grp.dense, grp2.dense)
         ctx.custom_saved_tensors = (gateW, gateW_quant, gateS, upW, upW_quant, upS, downW,
                                     downW_quant, downS, _backward_function)
         # LoRA A/B are kept as the caller's Parameter objects (not through save_for_backward) so
@@ -228,7 +238,11 @@ class LoRA_MLP(torch.autograd.Function):
         down = _Group(e, [(downW, downW_quant, downA, downB, downS)])  # in_f = I (e is [T, I])
         G_down = None
         segs = []
-        Wd = dense_weight(downW, downW_quant, dt, 0)                   # [H, I]
+        dense_gu, dense_down = ctx.dense
+        ctx.dense = None
+        Wd = dense_down[0] if dense_down is not None and dense_down[0] is not None else \
+            dense_weight(downW, downW_quant, dt, 0)                    # [H, I]
+        dense_down = None
         Bop, b_mn = as_b_operand(Wd.t())
         if not b_mn:
             Bop, b_mn = Bop.t().contiguous(), True
@@ -258,6 +272,7 @@ class LoRA_MLP(torch.autograd.Function):
             d_downA, d_downB = dA_T[:, :r].t(), dB_full[:, :r]
         # --- gate / up: LoRA grads and dX (into the saved X buffer when inplace)   (:178-204)
         grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
+        grp.dense = dense_gu
         dX, ((d_gateA, d_gateB), (d_upA, d_upB)) = grp.backward(
             [de, df], XA1, dX_out=X2 if ctx.inplace else None)
         return (dX.view(ctx.shape), None, None, d_gateA, d_gateB, None, None, None, d_upA, d_upB,
@@ -306,7 +321,8 @@ class LoRA_QKV(torch.autograd.Function):
         X2 = _as2d(X)
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
                           (VW, VW_quant, VA, VB, VS)])
-        (Q, K, V), XA = grp.forward()
+        (Q, K, V), XA = grp.forward(keep_dequant() and any(ctx.needs_input_grad))
+        ctx.dense = grp.dense
         if len(shape) == 3:
             Q, K, V = (t.view(shape[0], shape[1], -1) for t in (Q, K, V))
         ctx.custom_saved_tensors = (QW, QW_quant, QS, KW, KW_quant, KS, VW, VW_quant, VS)
@@ -324,6 +340,7 @@ class LoRA_QKV(torch.autograd.Function):
         X2, XA = ctx.saved_tensors
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
                           (VW, VW_quant, VA, VB, VS)])
+        grp.dense, ctx.dense = ctx.dense, None
         need_dX = ctx.needs_input_grad[0]     # False for the first layer (embedding output)
         dX, ((dQA, dQB), (dKA, dKB), (dVA, dVB)) = grp.backward(
             [_as2d(dQ), _as2d(dK), _as2d(dV)], XA, dX_out=X2 if ctx.inplace else None, need_dX=need_dX)
@@ -350,7 +367,8 @@ class LoRA_W(torch.autograd.Function):
         shape = X.shape
         X2 = _as2d(X)
         grp = _Group(X2, [(W, W_quant, A, B, S)])
-        (XW,), XA = grp.forward()
+        (XW,), XA = grp.forward(keep_dequant() and any(ctx.needs_input_grad))
+        ctx.dense = grp.dense
         ctx.custom_saved_tensors = (W, W_quant, S)
         ctx.lora = (A, B)
         ctx.save_for_backward(X2, XA)
@@ -364,6 +382,7 @@ class LoRA_W(torch.autograd.Function):
         A, B = ctx.lora
         X2, XA = ctx.saved_tensors
         grp = _Group(X2, [(W, W_quant, A, B, S)])
+        grp.dense, ctx.dense = ctx.dense, None
         dX, ((dA, dB),) = grp.backward([_as2d(dY)], XA)
         return dX.view(ctx.shape), None, None, dA, dB, None
 

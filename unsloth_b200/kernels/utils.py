@@ -5,6 +5,8 @@ consumers of the same NF4 format, `fast_gemv` (:874-973) and `fast_linear_forwar
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib as L
@@ -250,12 +252,46 @@ def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpos
     return dst
 
 
-def dense_weight(W, W_quant, dtype, slot=0):
+def keep_dequant() -> bool:
+    """Memory-for-bandwidth policy of the training step (B200: 180 GB of HBM3e).  When on, the
+    16-bit expansion of an NF4 weight made for the forward GEMM stays resident until that layer's
+    backward instead of being rebuilt there (the reference re-dequantises, fast_lora.py:193-204):
+    half of the step's dequant launches disappear for +2 bytes per base parameter of peak memory
+    (13.96 GB on Llama-3-8B).  UB200_KEEP_DEQUANT=1/0 forces it; the default turns it on for
+    devices with at least 128 GiB."""
+    global _KEEP_DEQUANT
+    if _KEEP_DEQUANT is None:
+        env = os.environ.get("UB200_KEEP_DEQUANT", "auto").lower()
+        if env in ("0", "off", "false"):
+            _KEEP_DEQUANT = False
+        elif env in ("1", "on", "true"):
+            _KEEP_DEQUANT = True
+        else:
+            _KEEP_DEQUANT = (torch.cuda.is_available()
+                             and torch.cuda.get_device_properties(0).total_memory >= 128 * 2 ** 30)
+    return _KEEP_DEQUANT
+
+
+def set_keep_dequant(value):
+    """True / False / None (= re-read UB200_KEEP_DEQUANT / the device-size default)."""
+    global _KEEP_DEQUANT
+    _KEEP_DEQUANT = value
+
+
+_KEEP_DEQUANT = None
+
+
+def dense_weight(W, W_quant, dtype, slot=0, fresh=False):
     """Logical [N_out, K_in] weight in the compute dtype, exactly what the reference's
     `fast_dequantize(W, W_quant)` hands to `torch.matmul(X, W.t())`: a reusable-slot dequantised
     buffer (a transposed VIEW of it when the packed weight was passed as `W.t()`), or W itself
-    for 16-bit LoRA."""
-    Wd = fast_dequantize(W, W_quant, use_global_buffer=True, _slot=slot) if W_quant is not None else W
+    for 16-bit LoRA.  `fresh`: a private tensor the caller may keep (see keep_dequant)."""
+    if W_quant is None:
+        Wd = W
+    elif fresh:
+        Wd = fast_dequantize(W, W_quant)
+    else:
+        Wd = fast_dequantize(W, W_quant, use_global_buffer=True, _slot=slot)
     if Wd.dtype != dtype:
         Wd = Wd.to(dtype)
     return Wd
