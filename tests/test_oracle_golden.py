@@ -165,3 +165,24 @@ def test_packing_label_vector(golden):
     from unsloth_b200.packing import mask_packed_boundary_labels
     out = mask_packed_boundary_labels(T(g["labels"])[None].clone(), T(g["packed_seq_lengths"]))
     assert out[0].tolist() == g["expected"].tolist()
+
+
+def test_oracle_gemv_restatement_matches_its_dequant():
+    """`gemv_nf4` / `fast_linear_forward` (decode path, kernels/utils.py:874-973, :1082-1125) are the
+    same NF4 expansion as `dequantize_nf4`, contracted with x: the two restatements must agree to
+    the rounding of the 16-bit dequantised weights."""
+    import torch
+    from oracle import restate as R
+    torch.manual_seed(0)
+    W = (torch.randn(96, 256) * 0.02).to(torch.bfloat16)
+    p, qs = R.quantize_nf4(W)
+    x = torch.randn(256).to(torch.bfloat16)
+    y = R.gemv_nf4(x, p, qs).float()
+    yd = R.dequantize_nf4(p, qs).float() @ x.float()
+    assert (y - yd).abs().max() <= 8e-3 * yd.abs().max()
+    A = torch.randn(8, 256) * 0.05
+    B = torch.randn(96, 8) * 0.05
+    full = R.fast_linear_forward(x, p, qs, A, B, 2.0).float()
+    ref = yd + 2.0 * (B.to(torch.bfloat16).float() @ (A.to(torch.bfloat16).float() @ x.float()))
+    assert (full - ref).abs().max() <= 8e-3 * ref.abs().max()
+    assert (full - y).abs().max() > 1e-2 * ref.abs().max()          # the LoRA term is present
