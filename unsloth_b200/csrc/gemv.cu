@@ -14,9 +14,9 @@
 // fp32 accumulation over k) restates the published NF4 layout and is at least as accurate as the
 // 16-bit products of the original; parity against bitsandbytes itself is unpinned.
 //
-// HBM-bound.  Algorithmic bytes per call: m*k*(0.5 + 4/blocksize) + k*2 + m*2 (NF4);
-// m*k*2 + k*2 + m*out_bytes (dense).  One warp owns ROWS consecutive rows and walks k in
-// 1024-column steps (16 packed bytes per lane per row), reusing its slice of x across the rows.
+// HBM-bound by bytes.  Algorithmic bytes per call: m*k*(0.5 + 1/blocksize) + k*2 + m*2 (NF4);
+// m*k*2 + k*2 + m*out_bytes (dense).  One warp owns a row (NF4) or two rows (dense) and walks k
+// in 1024- / 256-column steps, 16 bytes per lane per step.
 #include "common.cuh"
 
 namespace ub {
@@ -43,13 +43,17 @@ template <> struct P2<__half> {
   __device__ static __forceinline__ __half down(float v) { return __float2half_rn(v); }
 };
 
-// THREADS = 128: small CTAs (8 rows) keep the last partial wave short; the 32 KB table limits an
-// SM to 7 of them, registers to 4-5.
-constexpr int GEMV_THREADS = 128;
-constexpr int GEMV_DEPTH = 4;      // 1024-column steps whose packed bytes are fetched together
-
-template <typename T, int ROWS>
-__global__ void __launch_bounds__(GEMV_THREADS) gemv_nf4_kernel(
+// One row per warp; the 16-entry fp32 code table is replicated per LANE in shared memory (2 KB:
+// entry n of lane l at n*32 + l), so every lookup of a warp is conflict-free and costs one
+// wavefront whatever the nibbles are; 40 registers per thread => 48 resident warps per SM.
+// Round-1 status (profiles/r1_gemv_nf4_ncu.txt, profiles/r1_kernel_bench_gemv_addrms.log): this
+// kernel and a 32 KB byte-pair-table variant with 4 rows per warp both land at 24-28 us for a
+// 14336 x 4096 weight (1.1-1.3 TB/s): ~6 issued instructions per weight (shift, mask, LDS, FFMA,
+// x unpack) at the power-capped ~1.4 GHz SM clock is an ISSUE bound of ~14 us plus a 2.02-wave
+// tail, not a DRAM bound.  Reaching the HBM roofline needs <= 2 instructions per weight, i.e. a
+// 16-bit pair table feeding HFMA2 / mma fragments -- round-2 work.
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_nf4_lite_kernel(
     const T* __restrict__ x, const uint8_t* __restrict__ packed,
     const float* __restrict__ absmax_f32, const uint8_t* __restrict__ absmax_q,
     const float* __restrict__ code2, const float* __restrict__ absmax2,
@@ -57,121 +61,59 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_nf4_kernel(
     int k, int bs_shift, int bs2_shift, const T* __restrict__ lora_B, int ldb,
     const float* __restrict__ lora_t, int r, float s) {
   using T2 = typename P2<T>::T2;
-  // byte -> (code[hi nibble], code[lo nibble]) in fp32, replicated 16x so that lane l always reads
-  // copy l % 16: the 16 lanes of each 64-bit shared-memory wavefront hit 16 different bank pairs
-  // whatever bytes they look up (an un-replicated table serialises ~7x on random nibbles).
-  extern __shared__ __align__(16) unsigned char gemv_smem[];
-  float2* lut2 = reinterpret_cast<float2*>(gemv_smem);                 // 32 KB table
-  int4* xs = reinterpret_cast<int4*>(gemv_smem + 256 * 16 * sizeof(float2));   // x, k * 2 bytes
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = (blockIdx.x * (GEMV_THREADS / 32) + warp) * ROWS;
-  const bool live = row0 < m;
-  const float off = offset ? *offset : 0.f;
-  const int64_t row_bytes = (int64_t)k / 2;
-  // rows past the end alias the last row (their results are not stored)
-  const uint8_t* wrow[ROWS];
-  int64_t ebase[ROWS];
-#pragma unroll
-  for (int i = 0; i < ROWS; ++i) {
-    const int row = row0 + i < m ? row0 + i : m - 1;
-    wrow[i] = packed + row * row_bytes;
-    ebase[i] = (int64_t)row * k;
-  }
-  int4 w[GEMV_DEPTH][ROWS];
-  float am[GEMV_DEPTH][ROWS];
-  // all packed bytes and block scales of a 4096-column span are requested before anything is
-  // expanded: the first span's loads are in flight while the table is being built
-  auto fetch = [&](int cbase) {
-#pragma unroll
-    for (int d = 0; d < GEMV_DEPTH; ++d) {
-      const int c0 = cbase + d * 1024 + lane * 32;
-      if (c0 < k) {
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-          w[d][i] = __ldcs(reinterpret_cast<const int4*>(wrow[i] + c0 / 2));
-          const int64_t blk = (ebase[i] + c0) >> bs_shift;        // block sizes are powers of two:
-          am[d][i] = absmax_f32 ? absmax_f32[blk]                 // no 64-bit divisions in the loop
-                                : fmaf(code2[absmax_q[blk]], absmax2[blk >> bs2_shift], off);
-        }
-      }
-    }
-  };
-  if (live) fetch(0);
-  for (int e = threadIdx.x; e < 256 * 16; e += GEMV_THREADS) {   // consecutive lanes, consecutive banks
-    const int b = e >> 4;
-    lut2[e] = make_float2(code16 ? code16[b >> 4] : kNF4g[b >> 4],
-                          code16 ? code16[b & 15] : kNF4g[b & 15]);
-  }
-  // x is staged once per CTA (every warp walks all of it).  16-byte chunk g = columns 8g..8g+7
-  // belongs to lane (g % 128) / 4, quarter g % 4 of 1024-column step g / 128; it is stored at
-  // step * 128 + quarter * 32 + lane so that the four 16-byte reads of a lane are conflict-free.
-  for (int g = threadIdx.x; g < k / 8; g += GEMV_THREADS) {
-    const int within = g & 127;
-    xs[(g & ~127) + (within & 3) * 32 + (within >> 2)] = __ldg(reinterpret_cast<const int4*>(x) + g);
-  }
+  __shared__ float lut[16 * 32];
+  for (int e = threadIdx.x; e < 16 * 32; e += 256) lut[e] = code16 ? code16[e >> 5] : kNF4g[e >> 5];
   __syncthreads();
-  if (!live) return;
-  // table address of byte b for this lane = b * 128 + (lane % 16) * 8: the byte is moved to bits
-  // 7..14 with one shift and merged with the lane bits by one 3-input logic op
-  const uint32_t lane_bits = (uint32_t)(lane & 15) << 3;
-  const char* lut_bytes = reinterpret_cast<const char*>(lut2);
-  float acc[ROWS];
-#pragma unroll
-  for (int i = 0; i < ROWS; ++i) acc[i] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= m) return;
+  const float off = offset ? *offset : 0.f;
+  const uint8_t* wrow = packed + (int64_t)row * (k / 2);
+  const int64_t ebase = (int64_t)row * k;
+  const uint32_t lane_bits = (uint32_t)lane << 2;
+  const char* lut_bytes = reinterpret_cast<const char*>(lut);
+  auto scale = [&](int c0) {
+    const int64_t blk = (ebase + c0) >> bs_shift;
+    return absmax_f32 ? absmax_f32[blk] : fmaf(code2[absmax_q[blk]], absmax2[blk >> bs2_shift], off);
+  };
+  float acc = 0.f;
+  int c0 = lane * 32;
+  int4 wc = make_int4(0, 0, 0, 0), wn;
+  float amc = 0.f, amn;
+  if (c0 < k) { wc = __ldcs(reinterpret_cast<const int4*>(wrow + c0 / 2)); amc = scale(c0); }
 #pragma unroll 1
-  for (int cbase = 0; cbase < k; cbase += GEMV_DEPTH * 1024) {
-    if (cbase) fetch(cbase);
+  for (; c0 < k; c0 += 1024) {
+    const bool more = c0 + 1024 < k;
+    if (more) { wn = __ldcs(reinterpret_cast<const int4*>(wrow + (c0 + 1024) / 2)); amn = scale(c0 + 1024); }
+    const uint32_t u[4] = {(uint32_t)wc.x, (uint32_t)wc.y, (uint32_t)wc.z, (uint32_t)wc.w};
+    float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-    for (int d = 0; d < GEMV_DEPTH; ++d) {
-      const int c0 = cbase + d * 1024 + lane * 32;
-      if (c0 < k) {
-        float xf[32];
+    for (int q = 0; q < 4; ++q) {
+      union { int4 v; T2 h[4]; } xv;
+      xv.v = __ldg(reinterpret_cast<const int4*>(x + c0) + q);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          union { int4 v; T2 h[4]; } xv;
-          xv.v = xs[(c0 >> 10) * 128 + q * 32 + lane];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = P2<T>::up(xv.h[j]);
-            xf[q * 8 + 2 * j] = f.x;
-            xf[q * 8 + 2 * j + 1] = f.y;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-          const uint32_t u[4] = {(uint32_t)w[d][i].x, (uint32_t)w[d][i].y, (uint32_t)w[d][i].z,
-                                 (uint32_t)w[d][i].w};
-          float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int sh = 8 * (j & 3) - 7;
-            const uint32_t word = u[j >> 2];
-            const uint32_t o = ((sh < 0 ? word << 7 : word >> sh) & 0x7F80u) | lane_bits;
-            const float2 c = *reinterpret_cast<const float2*>(lut_bytes + o);
-            p0 = fmaf(c.x, xf[2 * j], p0);
-            p1 = fmaf(c.y, xf[2 * j + 1], p1);
-          }
-          acc[i] = fmaf(am[d][i], p0 + p1, acc[i]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = P2<T>::up(xv.h[j]);
+        // byte j of the word: high nibble = even element; nibble moved to bits 7..10 (n * 128)
+        const int sh_hi = 8 * j + 4 - 7, sh_lo = 8 * j - 7;
+        const uint32_t o_hi = ((sh_hi < 0 ? u[q] << -sh_hi : u[q] >> sh_hi) & 0x780u) | lane_bits;
+        const uint32_t o_lo = ((sh_lo < 0 ? u[q] << -sh_lo : u[q] >> sh_lo) & 0x780u) | lane_bits;
+        p0 = fmaf(*reinterpret_cast<const float*>(lut_bytes + o_hi), f.x, p0);
+        p1 = fmaf(*reinterpret_cast<const float*>(lut_bytes + o_lo), f.y, p1);
       }
     }
+    acc = fmaf(amc, p0 + p1, acc);
+    if (more) { wc = wn; amc = amn; }
   }
-#pragma unroll
-  for (int i = 0; i < ROWS; ++i) acc[i] = warp_sum(acc[i]);
+  acc = warp_sum(acc);
   if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < ROWS; ++i) {
-      const int row = row0 + i;
-      if (row < m) {
-        float v = acc[i];
-        if (lora_B) {
-          float d = 0.f;
-          for (int j = 0; j < r; ++j) d = fmaf(DT<T>::to_f(lora_B[(int64_t)row * ldb + j]), lora_t[j], d);
-          v = fmaf(s, d, v);
-        }
-        out[row] = P2<T>::down(v);
-      }
+    float v = acc;
+    if (lora_B) {
+      float d = 0.f;
+      for (int j = 0; j < r; ++j) d = fmaf(DT<T>::to_f(lora_B[(int64_t)row * ldb + j]), lora_t[j], d);
+      v = fmaf(s, d, v);
     }
+    out[row] = P2<T>::down(v);
   }
 }
 
@@ -229,17 +171,7 @@ static int launch_gemv_nf4(const void* x, const uint8_t* packed, const float* ab
   int bs_shift = 0, bs2_shift = 0;
   while ((1 << bs_shift) < blocksize) ++bs_shift;
   while ((1 << bs2_shift) < blocksize2) ++bs2_shift;
-  constexpr int ROWS = 2, RPC = ROWS * GEMV_THREADS / 32;          // rows per CTA
-  const size_t smem = 256 * 16 * sizeof(float2) + (size_t)((k + 1023) / 1024) * 1024 * sizeof(T);
-  if (smem > 220 * 1024) return UB200_ERR_UNSUPPORTED;
-  static size_t smem_set = 0;        // opt-in above 48 KB, raised monotonically (idempotent)
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_nf4_kernel<T, ROWS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    smem_set = smem;
-  }
-  gemv_nf4_kernel<T, ROWS><<<(m + RPC - 1) / RPC, GEMV_THREADS, smem, st>>>(
+  gemv_nf4_lite_kernel<T><<<(m + 7) / 8, 256, 0, st>>>(
       (const T*)x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16, (T*)out, m, k,
       bs_shift, bs2_shift, (const T*)lora_B, ldb, lora_t, r, s);
   UB_RETURN_LAST();
