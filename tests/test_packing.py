@@ -53,3 +53,22 @@ def test_packed_info_and_position_ids():
     except ValueError:
         pass
     clear_packed_caches()
+
+
+def test_keep_dequant_policy_switch(monkeypatch):
+    """UB200_KEEP_DEQUANT=0/1 forces the residency policy of the dequantised weights; without a
+    CUDA device the automatic default is off (the policy keys on >= 128 GiB of device memory)."""
+    from unsloth_b200.kernels import utils as KU
+    try:
+        for env, want in (("0", False), ("off", False), ("1", True), ("on", True)):
+            monkeypatch.setenv("UB200_KEEP_DEQUANT", env)
+            KU.set_keep_dequant(None)
+            assert KU.keep_dequant() is want
+        monkeypatch.delenv("UB200_KEEP_DEQUANT")
+        KU.set_keep_dequant(None)
+        if not torch.cuda.is_available():
+            assert KU.keep_dequant() is False
+        KU.set_keep_dequant(True)
+        assert KU.keep_dequant() is True
+    finally:
+        KU.set_keep_dequant(None)

@@ -21,8 +21,8 @@ import torch
 
 from .. import _lib as L
 from .utils import (RANK_BLOCK, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
-                    keep_dequant,
-                    get_lora_parameters, get_lora_parameters_bias, matmul_lora)  # noqa: F401
+                    keep_dequant, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
+                    matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
 from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
                     geglu_approx_forward_kernel, geglu_approx_backward_kernel)
