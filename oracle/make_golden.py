@@ -209,8 +209,58 @@ def gen_reference_tests(k):
          labels=np.arange(8), expected=np.array([-100, 1, 2, -100, 4, 5, 6, 7]))
 
 
+def gen_fp16_rounding_points(k):
+    """16-bit runs of the reference kernels (fp16: the interpreter has no bf16).  They pin the
+    ROUNDING POINTS of SURVEY.md section 9 that fp32 vectors cannot see: `normed -> W.dtype`
+    (rms_layernorm.py:57), `f -> g.dtype` (swiglu.py:42, geglu.py:161), the table-dtype products
+    of RoPE (rope_embedding.py:129-158) and the in-place 16-bit CE gradient
+    (cross_entropy_loss.py:245-276).  The GPU bf16 gates compare against the oracle's emulation
+    of exactly these points."""
+    g = torch.Generator().manual_seed(SEED + 7)
+    H = 256
+    X = torch.randn(2, 5, H, generator=g).half()
+    W = (torch.randn(H, generator=g) * 0.5 + 1).half()
+    dY = torch.randn(2, 5, H, generator=g).half()
+    Xr = X.clone().requires_grad_()
+    Y = k.rms_layernorm.fast_rms_layernorm(_Norm(W, 1e-5), Xr, gemma=False)
+    Yc = Y.detach().clone()
+    Y.backward(dY.clone())
+    save("fp16_rms_llama", X=X, W=W, dY=dY, Y=Yc, dX=Xr.grad, eps=1e-5)
+    I = 300
+    e = (torch.randn(2, 5, I, generator=g) * 2).half()
+    up = torch.randn(2, 5, I, generator=g).half()
+    DW = torch.randn(10, I, generator=g).half()
+    for name, fwd, bwd in (
+            ("swiglu", k.swiglu.swiglu_fg_kernel, k.swiglu.swiglu_DWf_DW_dfg_kernel),
+            ("geglu_approx", k.geglu.geglu_approx_forward_kernel, k.geglu.geglu_approx_backward_kernel),
+            ("geglu_exact", k.geglu.geglu_exact_forward_kernel, k.geglu.geglu_exact_backward_kernel)):
+        h = fwd(e.clone(), up.clone())
+        h2, df, de = bwd(DW.clone(), e.reshape(-1, I).clone(), up.reshape(-1, I).clone())
+        save("fp16_" + name, e=e, g=up, DW=DW, h=h, bh=h2, bdf=df, bde=de)
+    B, S, Hq, Hk, D = 2, 9, 6, 2, 64
+    cos, sin = _rope_tables(16, D, g)
+    cos, sin = cos.half(), sin.half()
+    Q = torch.randn(B, Hq, S, D, generator=g).half()
+    K = torch.randn(B, Hk, S, D, generator=g).half()
+    Qo, Ko = k.rope_embedding.fast_rope_embedding(Q.clone(), K.clone(), cos, sin)
+    idx = torch.randint(0, 16, (B * S,), generator=g).to(torch.int32)
+    Qi, Ki = k.rope_embedding.fast_rope_embedding(Q.clone(), K.clone(), cos, sin, idx)
+    save("fp16_rope", Q=Q, K=K, cos=cos, sin=sin, idx=idx, Qo=Qo.detach(), Ko=Ko.detach(),
+         Qi=Qi.detach(), Ki=Ki.detach())
+    T_, V = 6, 1200
+    logits = (torch.randn(1, T_, V, generator=g) * 4).half()
+    labels = torch.randint(0, V, (1, T_), generator=g)
+    labels[0, 2] = -100
+    lr = logits.clone().requires_grad_()
+    loss = k.cross_entropy_loss.fast_cross_entropy_loss(lr, labels, 0.0, 0.0)
+    loss_c = loss.detach().clone()
+    loss.backward()
+    save("fp16_ce", logits=logits, labels=labels, loss=loss_c, dlogits=lr.grad.clone())
+
+
 def main():
     k = load_reference_kernels()
+    gen_fp16_rounding_points(k)
     gen_rmsnorm(k)
     gen_rope(k)
     gen_ce(k)

@@ -186,3 +186,64 @@ def test_oracle_gemv_restatement_matches_its_dequant():
     ref = yd + 2.0 * (B.to(torch.bfloat16).float() @ (A.to(torch.bfloat16).float() @ x.float()))
     assert (full - ref).abs().max() <= 8e-3 * ref.abs().max()
     assert (full - y).abs().max() > 1e-2 * ref.abs().max()          # the LoRA term is present
+
+
+# ----------------------------------------------------------------------------------------------
+# 16-bit rounding points: the reference's Triton kernels run in fp16 under
+# the interpreter; the oracle's emulation of every rounding point must reproduce them to the last
+# bit up to FMA-contraction / libm noise: at most one fp16 ulp on at most 0.5 % of the elements.
+# ----------------------------------------------------------------------------------------------
+def ulp_close(ours, ref, max_frac=5e-3, max_ulps=1):
+    ours, ref = ours.detach(), T(ref) if not torch.is_tensor(ref) else ref
+    assert ours.dtype == torch.float16 and ref.dtype == torch.float16
+    a, b = ours.float().reshape(-1), ref.float().reshape(-1)
+    ulp = torch.maximum(b.abs(), torch.tensor(6.1e-5)) * 2.0 ** -10      # fp16: 10 stored mantissa bits
+    bad = (a - b).abs() > 0
+    assert bad.float().mean().item() <= max_frac, bad.float().mean().item()
+    # 1e-6 absolute floor: the subnormal tail, where (1 + erf) / (1 + tanh) cancel catastrophically
+    ok = ((a - b).abs() <= (max_ulps + 0.001) * ulp) | ((a - b).abs() <= 1e-6)
+    assert ok.all(), ((a - b).abs() / ulp).max().item()
+
+
+def test_fp16_rounding_points_rmsnorm(golden):
+    g = golden("fp16_rms_llama")
+    X, W, dY = T(g["X"]), T(g["W"]), T(g["dY"])
+    Y, r = R.rms_layernorm_fwd(X, W, float(g["eps"]), False)
+    ulp_close(Y, g["Y"], max_frac=0.0)                 # `normed -> W.dtype` then `* W`: bit exact
+    ulp_close(R.rms_layernorm_bwd(dY, X, W, r, False), g["dX"])
+
+
+@pytest.mark.parametrize("name,fwd,bwd", [
+    ("fp16_swiglu", R.swiglu_fwd, R.swiglu_bwd),
+    ("fp16_geglu_approx", R.geglu_approx_fwd, R.geglu_approx_bwd),
+    ("fp16_geglu_exact", R.geglu_exact_fwd, R.geglu_exact_bwd)])
+def test_fp16_rounding_points_glu(golden, name, fwd, bwd):
+    g = golden(name)
+    e, up, DW = T(g["e"]), T(g["g"]), T(g["DW"])
+    # tanh / erf come from different libms (Triton interpreter vs torch): allow 2 / 4 ulps there
+    mu = {"fp16_swiglu": 1, "fp16_geglu_approx": 2, "fp16_geglu_exact": 4}[name]
+    ulp_close(fwd(e, up), g["h"], max_ulps=mu)
+    h, df, de = bwd(DW, e.reshape(-1, e.shape[-1]), up.reshape(-1, up.shape[-1]))
+    ulp_close(h, g["bh"], max_ulps=mu); ulp_close(df, g["bdf"], max_ulps=mu); ulp_close(de, g["bde"], max_ulps=mu)
+
+
+def test_fp16_rounding_points_rope(golden):
+    g = golden("fp16_rope")
+    Q, K, cos, sin, idx = (T(g[k]) for k in ("Q", "K", "cos", "sin", "idx"))
+    Qo = R.rope_noindex(Q.transpose(1, 2), cos, sin).transpose(1, 2)
+    Ko = R.rope_noindex(K.transpose(1, 2), cos, sin).transpose(1, 2)
+    ulp_close(Qo, g["Qo"]); ulp_close(Ko, g["Ko"])
+    Qi, Ki = R.rope_qk(Q, K, cos, sin, idx)
+    ulp_close(Qi, g["Qi"]); ulp_close(Ki, g["Ki"])
+
+
+def test_fp16_rounding_points_cross_entropy(golden):
+    g = golden("fp16_ce")
+    logits, labels = T(g["logits"]), T(g["labels"])
+    V = logits.shape[-1]
+    loss, lse = R.cross_entropy_fwd(logits.view(-1, V), labels.view(-1), 0.0, 0.0)
+    n = (labels != -100).sum()
+    close(loss.sum() / n, g["loss"], rtol=1e-5, atol=1e-5)
+    dl = torch.full((labels.numel(),), 1.0 / n.item())
+    dlog = R.cross_entropy_bwd(logits.view(-1, V), lse, labels.view(-1), dl, 0.0, 0.0)
+    ulp_close(dlog.view_as(logits), g["dlogits"], max_frac=2e-2)
