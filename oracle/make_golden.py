@@ -258,9 +258,61 @@ def gen_fp16_rounding_points(k):
     save("fp16_ce", logits=logits, labels=labels, loss=loss_c, dlogits=lr.grad.clone())
 
 
+def gen_fp16_lora(k):
+    """fp16 runs of LoRA_W / LoRA_QKV / LoRA_MLP (16-bit X and W, fp32 adapters as PEFT keeps
+    them): pin the rounding points of `matmul_lora` (utils.py:1158-1168: base product -> 16 bit,
+    XA -> 16 bit, addmm_ -> 16 bit) and of the LoRA gradients (fast_lora.py:172-204, 476-517,
+    639-647) that SURVEY section 9 lists."""
+    g = torch.Generator().manual_seed(SEED + 8)
+    fl = k.fast_lora
+
+    def lora(out_f, in_f, r, s):
+        W = (torch.randn(out_f, in_f, generator=g) * 0.05).half()
+        A = ((torch.rand(r, in_f, generator=g) * 2 - 1) / (in_f ** 0.5)).requires_grad_()
+        B = (torch.randn(out_f, r, generator=g) * 0.02).requires_grad_()
+        return W, A, B, s
+    Bz, S, H, I, r = 2, 6, 64, 160, 8
+    X = torch.randn(Bz, S, H, generator=g).half()
+    dY = torch.randn(Bz, S, H, generator=g).half()
+    oW, oA, oB, os_ = lora(H, H, r, 1.0)
+    Xr = X.clone().requires_grad_()
+    O = fl.LoRA_W.apply(Xr, oW, None, oA, oB, os_)
+    Oc = O.detach().clone()
+    O.backward(dY.clone())
+    save("fp16_lora_w", X=X, dY=dY, oW=oW, oA=oA, oB=oB, s=1.0, O=Oc, dX=Xr.grad,
+         d_oA=oA.grad, d_oB=oB.grad)
+    nq, nk = 96, 32
+    qW, qA, qB, qs = lora(nq, H, r, 0.5)
+    kW, kA, kB, ks = lora(nk, H, r, 0.5)
+    vW, vA, vB, vs = lora(nk, H, r, 0.5)
+    dQ = torch.randn(Bz, S, nq, generator=g).half()
+    dK = torch.randn(Bz, S, nk, generator=g).half()
+    dV = torch.randn(Bz, S, nk, generator=g).half()
+    Xr = X.clone().requires_grad_()
+    Q, K, V = fl.LoRA_QKV.apply(Xr, qW, None, qA, qB, qs, kW, None, kA, kB, ks,
+                                vW, None, vA, vB, vs, False)
+    Qc, Kc, Vc = Q.detach().clone(), K.detach().clone(), V.detach().clone()
+    torch.autograd.backward([Q, K, V], [dQ.clone(), dK.clone(), dV.clone()])
+    save("fp16_lora_qkv", X=X, dQ=dQ, dK=dK, dV=dV, qW=qW, qA=qA, qB=qB, kW=kW, kA=kA, kB=kB,
+         vW=vW, vA=vA, vB=vB, s=0.5, Q=Qc, K=Kc, V=Vc, dX=Xr.grad,
+         d_qA=qA.grad, d_qB=qB.grad, d_kA=kA.grad, d_kB=kB.grad, d_vA=vA.grad, d_vB=vB.grad)
+    gW, gA, gB, gs = lora(I, H, r, 2.0)
+    uW, uA, uB, us = lora(I, H, r, 2.0)
+    dW, dA, dB, ds = lora(H, I, r, 2.0)
+    Xr = X.clone().requires_grad_()
+    out = fl.LoRA_MLP.apply(Xr, gW, None, gA, gB, gs, uW, None, uA, uB, us, dW, None, dA, dB, ds,
+                            k.swiglu.swiglu_fg_kernel, k.swiglu.swiglu_DWf_DW_dfg_kernel, False)
+    out_c = out.detach().clone()
+    out.backward(dY.clone())
+    save("fp16_lora_mlp_swiglu", X=X, dY=dY, gW=gW, gA=gA, gB=gB, uW=uW, uA=uA, uB=uB,
+         dW=dW, dA=dA, dB=dB, s=2.0, out=out_c, dX=Xr.grad,
+         d_gA=gA.grad, d_gB=gB.grad, d_uA=uA.grad, d_uB=uB.grad, d_dA=dA.grad, d_dB=dB.grad)
+
+
 def main():
     k = load_reference_kernels()
     gen_fp16_rounding_points(k)
+    gen_fp16_lora(k)
     gen_rmsnorm(k)
     gen_rope(k)
     gen_ce(k)

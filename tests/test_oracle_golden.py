@@ -247,3 +247,46 @@ def test_fp16_rounding_points_cross_entropy(golden):
     dl = torch.full((labels.numel(),), 1.0 / n.item())
     dlog = R.cross_entropy_bwd(logits.view(-1, V), lse, labels.view(-1), dl, 0.0, 0.0)
     ulp_close(dlog.view_as(logits), g["dlogits"], max_frac=2e-2)
+
+
+def _eq16(mine, ref, what):
+    """LoRA rounding points in 16 bit: the reference's functions and the oracle do the same fp32-
+    accumulated products and round at the same places, so results agree to the bit (a 1-ulp
+    difference on <= 0.5 % of the elements is tolerated for BLAS summation-order noise)."""
+    ref = T(ref)
+    if ref.dtype == torch.float16:
+        ulp_close(mine, ref)
+    else:       # adapter gradients: 16-bit values stored in fp32 (SURVEY section 9)
+        torch.testing.assert_close(mine.float(), ref.float(), rtol=1e-3, atol=1e-6, msg=what)
+        assert (mine.float() != ref.float()).float().mean() <= 5e-3, what
+
+
+def test_fp16_rounding_points_lora(golden):
+    g = golden("fp16_lora_w")
+    t = {k: T(v) for k, v in g.items()}
+    o = (t["oW"], None, t["oA"], t["oB"], float(g["s"]))
+    _eq16(R.lora_w_fwd(t["X"], o), g["O"], "O")
+    dX, (dA, dB) = R.lora_w_bwd(t["dY"], t["X"], o)
+    _eq16(dX, g["dX"], "dX"); _eq16(dA, g["d_oA"], "dA"); _eq16(dB, g["d_oB"], "dB")
+
+    g = golden("fp16_lora_qkv")
+    t = {k: T(v) for k, v in g.items()}
+    s = float(g["s"])
+    q, k, v = ((t[n + "W"], None, t[n + "A"], t[n + "B"], s) for n in "qkv")
+    Q, K, V = R.lora_qkv_fwd(t["X"], q, k, v)
+    _eq16(Q, g["Q"], "Q"); _eq16(K, g["K"], "K"); _eq16(V, g["V"], "V")
+    dX, gq, gk, gv = R.lora_qkv_bwd(t["dQ"], t["dK"], t["dV"], t["X"], q, k, v)
+    _eq16(dX, g["dX"], "dX")
+    for (a, b), n in ((gq, "q"), (gk, "k"), (gv, "v")):
+        _eq16(a, g["d_%sA" % n], n + "A"); _eq16(b, g["d_%sB" % n], n + "B")
+
+    g = golden("fp16_lora_mlp_swiglu")
+    t = {k: T(v) for k, v in g.items()}
+    s = float(g["s"])
+    gate, up, down = ((t[n + "W"], None, t[n + "A"], t[n + "B"], s) for n in "gud")
+    out, e, gg = R.lora_mlp_fwd(t["X"], gate, up, down, "swiglu")
+    _eq16(out, g["out"], "out")
+    dX, (dgA, dgB), (duA, duB), (ddA, ddB) = R.lora_mlp_bwd(t["dY"], t["X"], e, gg, gate, up, down, "swiglu")
+    _eq16(dX, g["dX"], "dX")
+    for mine, key in ((dgA, "d_gA"), (dgB, "d_gB"), (duA, "d_uA"), (duB, "d_uB"), (ddA, "d_dA"), (ddB, "d_dB")):
+        _eq16(mine, g[key], key)
