@@ -4,8 +4,8 @@ metadata contract of unsloth/utils/packing.py:586-606."""
 import torch
 
 from unsloth_b200.packing import (clear_packed_caches, get_packed_info_from_kwargs,
-                                  mask_packed_boundary_labels, num_items_in_batch,
-                                  packed_position_ids)
+                                  mask_packed_boundary_labels, mask_packed_sequence_boundaries,
+                                  num_items_in_batch, packed_position_ids)
 
 
 def test_boundary_mask_values_pinned_by_reference_tests():
@@ -20,6 +20,42 @@ def test_boundary_mask_values_pinned_by_reference_tests():
     assert torch.equal(mask_packed_boundary_labels(once, lengths), once)
     assert mask_packed_boundary_labels(labels, None) is labels
     assert mask_packed_boundary_labels(labels, torch.tensor([], dtype=torch.int32)) is labels
+
+
+def test_boundary_mask_cases_of_the_reference_tests():
+    """tests/utils/test_packing.py:1375-1436, case by case."""
+    labels = torch.arange(6, dtype=torch.long).view(1, 6)
+    out = mask_packed_boundary_labels(labels, torch.tensor([2, 1, 3], dtype=torch.int32))
+    assert out.shape == labels.shape and out.dtype == labels.dtype
+    # the two entry points mask exactly the same CE targets (:1388-1406)
+    labels = torch.arange(100, 112, dtype=torch.long).view(1, 12)
+    lengths = torch.tensor([5, 4, 3], dtype=torch.int32)
+    shift_a = torch.empty_like(labels)
+    shift_a[..., :-1] = labels[..., 1:]
+    shift_a[..., -1] = -100
+    assert mask_packed_sequence_boundaries(shift_a, lengths) is True
+    masked = mask_packed_boundary_labels(labels, lengths)
+    shift_b = torch.empty_like(masked)
+    shift_b[..., :-1] = masked[..., 1:]
+    shift_b[..., -1] = -100
+    assert torch.equal(shift_a, shift_b)
+    # idempotent on TRL's labels[position_ids == 0] = -100 (:1409-1420)
+    lengths = torch.tensor([2, 1, 3], dtype=torch.int32)
+    labels = torch.arange(6, dtype=torch.long).view(1, 6)
+    trl = labels.clone()
+    trl[torch.tensor([[0, 1, 0, 0, 1, 2]]) == 0] = -100
+    once = mask_packed_boundary_labels(trl, lengths)
+    assert torch.equal(once, trl) and torch.equal(mask_packed_boundary_labels(once, lengths), once)
+    # no-op without packing (:1423-1427)
+    assert mask_packed_boundary_labels(None, torch.tensor([2, 4])) is None
+    assert mask_packed_sequence_boundaries(labels.clone(), None) is False
+    # pad_to_multiple_of tail stays -100, no index out of range (:1430-1434)
+    padded = torch.tensor([[10, 11, 12, 13, -100, -100]], dtype=torch.long)
+    out = mask_packed_boundary_labels(padded, torch.tensor([2, 2], dtype=torch.int32))
+    assert out.reshape(-1).tolist() == [10, 11, -100, 13, -100, -100]
+    # lengths covering the whole row: the redirect must not corrupt a real target (:1437-1441)
+    out = mask_packed_boundary_labels(torch.arange(4, dtype=torch.long).view(1, 4), [2, 2])
+    assert out.reshape(-1).tolist() == [-100, 1, -100, 3]
 
 
 def test_num_items_rule():

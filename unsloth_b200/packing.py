@@ -25,6 +25,25 @@ def mask_packed_boundary_labels(labels, seq_lengths, *, ignore_index: int = -100
     return labels.reshape(-1).index_fill(0, starts, ignore_index).view(labels.shape)
 
 
+def mask_packed_sequence_boundaries(shift_labels, seq_lengths, *, ignore_index: int = -100) -> bool:
+    """The in-place guard on ALREADY SHIFTED labels (unsloth/utils/packing.py:710-730), used by the
+    logits path (`fast_cross_entropy_loss` after the caller's shift, llama.py:1545-1552): the last
+    token of every packed document must not predict the next document's first token.  Returns
+    whether anything was masked."""
+    if seq_lengths is None:
+        return False
+    lengths = torch.as_tensor(seq_lengths, device=shift_labels.device).to(torch.int64).reshape(-1)
+    if lengths.numel() == 0:
+        return False
+    flat = shift_labels.reshape(-1)
+    boundary = torch.cumsum(lengths, dim=0) - 1
+    boundary = boundary[boundary < flat.shape[0]]
+    if boundary.numel() == 0:
+        return False
+    flat[boundary] = ignore_index
+    return True
+
+
 _PACKED_INFO_CACHE = {}
 
 
