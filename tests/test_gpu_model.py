@@ -162,6 +162,34 @@ def test_packed_row_equals_separate_documents(name, extra):
     assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.995
 
 
+@pytest.mark.skipif(__import__("os").environ.get("UB200_RUN_UNVALIDATED", "0") != "1",
+                    reason="written after the round-1 GPU budget was spent; not yet run on hardware "
+                           "(set UB200_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("name,extra", [("llama-3-8b", {}), ("gemma-2-9b", {"query_pre_attn_scalar": 64})])
+def test_return_logits_path_matches_fused_ce(name, extra, monkeypatch):
+    """UNSLOTH_RETURN_LOGITS=1 (models/llama.py:1525-1562: lm_head GEMM, caller-side shift, packed
+    guard on the shifted labels, `fast_cross_entropy_loss`) against the default logits-free path."""
+    from unsloth_b200.patch import build_qlora_model, lora_parameters
+    kw = dict(TINY, **extra)
+    model = build_qlora_model(name, r=8, lora_alpha=16, device=DEV, num_hidden_layers=2,
+                              init_b_std=0.05, **kw)
+    torch.manual_seed(2)
+    ids = torch.randint(0, kw["vocab_size"], (2, 64), device=DEV)
+    labels = ids.clone(); labels[1, :7] = -100
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("UNSLOTH_RETURN_LOGITS", flag)
+        for p_ in lora_parameters(model):
+            p_.grad = None
+        out = model(input_ids=ids, labels=labels)
+        out.loss.backward()
+        res[flag] = (out.loss.item(), torch.cat([p_.grad.flatten() for p_ in lora_parameters(model)]), out.logits)
+    assert res["0"][2] is None and res["1"][2].shape == (2, 64, kw["vocab_size"])
+    assert abs(res["0"][0] - res["1"][0]) <= 2e-3 * abs(res["0"][0])
+    a, b = res["1"][1], res["0"][1]
+    assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.999
+
+
 def test_sliding_window_and_softcap_route():
     """Mistral / Gemma-2 deltas go through flash-attn with the reference's arguments
     (mistral.py:112-128, gemma2.py:159): check against an explicit masked softmax."""

@@ -21,6 +21,7 @@ them with LoRA -- what `FastLanguageModel.from_pretrained(load_in_4bit=True)` +
 from __future__ import annotations
 
 import math
+import os
 import types
 from types import SimpleNamespace
 
@@ -29,7 +30,8 @@ import torch
 from . import kernels as K
 from .lora import LoraLinear
 from .nf4 import Linear4bit
-from .packing import get_packed_info_from_kwargs, mask_packed_boundary_labels, packed_position_ids
+from .packing import (get_packed_info_from_kwargs, mask_packed_boundary_labels,
+                      mask_packed_sequence_boundaries, packed_position_ids)
 
 # model shapes of BASELINE.json configs (public model cards)
 CONFIGS = {
@@ -219,6 +221,20 @@ def CausalLM_fast_forward(self, input_ids=None, labels=None, position_ids=None,
     """models/llama.py:1371-1590, the `labels is not None and not UNSLOTH_RETURN_LOGITS` branch:
     boundary-mask packed labels (:1483), logits-free fused CE (:1497-1509), EMPTY logits."""
     hidden = Model_fast_forward(self.model, input_ids, position_ids, packed_seq_lengths)
+    if os.environ.get("UNSLOTH_RETURN_LOGITS", "0") == "1":
+        # models/llama.py:1525-1562: materialise the logits (one tcgen05 GEMM against lm_head),
+        # shift the labels here, guard the packed boundaries on the SHIFTED labels, Triton-style CE.
+        logits = K.LoRA_W.apply(hidden, self.lm_head.weight, None, None, None, None)
+        loss = None
+        if labels is not None:
+            shift_labels = torch.empty_like(labels)
+            shift_labels[..., :-1] = labels[..., 1:]
+            shift_labels[..., -1] = -100
+            mask_packed_sequence_boundaries(shift_labels, packed_seq_lengths)
+            loss = K.fast_cross_entropy_loss(logits=logits, labels=shift_labels,
+                                             logit_softcapping=self._ub_final_softcap,
+                                             logit_scaling=0, n_items=num_items_in_batch)
+        return SimpleNamespace(loss=loss, logits=logits, hidden_states=None)
     if labels is None:
         return SimpleNamespace(loss=None, logits=None, hidden_states=hidden)
     labels = mask_packed_boundary_labels(labels, packed_seq_lengths)
