@@ -11,8 +11,55 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_functions():
     src = open(os.path.join(ROOT, "include", "unsloth_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = set(re.findall(r"\b(ub200_\w+|cdequantize_\w+)\s*\(", src))
+    names = set(re.findall(r"\b(ub200_\w+|cdequantize_\w+|cgemm_4bit_\w+)\s*\(", src))
     return sorted(names)
+
+
+def _header_prototypes():
+    """{name: (restype, [ctype kind per parameter])} parsed from the header; kinds: 'p' pointer /
+    cudaStream_t, 'l' int64_t, 'i' int, 'f' float.  The `#else` (plain C) duplicates of the typed
+    bitsandbytes prototypes are parsed too and must agree with the CUDA ones."""
+    src = open(os.path.join(ROOT, "include", "unsloth_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = {}
+    for m in re.finditer(r"\b(int|void)\s+(ub200_\w+|cdequantize_\w+|cgemm_4bit_\w+)\s*\(([^)]*)\)\s*;", src):
+        res, name, params = m.group(1), m.group(2), m.group(3).strip()
+        kinds = []
+        if params and params != "void":
+            for prm in params.split(","):
+                prm = " ".join(prm.split())
+                if "*" in prm or "cudaStream_t" in prm:
+                    kinds.append("p")
+                elif re.search(r"\bint64_t\b", prm):
+                    kinds.append("l")
+                elif re.search(r"\bfloat\b", prm):
+                    kinds.append("f")
+                elif re.search(r"\bint\b", prm):
+                    kinds.append("i")
+                else:
+                    raise AssertionError("unparsed parameter %r of %s" % (prm, name))
+        protos.setdefault(name, []).append((res, kinds))
+    return protos
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every ctypes signature in unsloth_b200/_lib.py has the header's parameter count, parameter
+    kinds (pointer / int64 / int / float) and return type: a mismatch would pass garbage silently."""
+    import ctypes
+    from unsloth_b200 import _lib
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib._SIGS), set(protos) ^ set(_lib._SIGS)
+
+    def kind(t):
+        if t in (ctypes.c_void_p,) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "p"
+        return {ctypes.c_int64: "l", ctypes.c_int: "i", ctypes.c_float: "f"}[t]
+    for name, variants in protos.items():
+        args, res = _lib._SIGS[name]
+        for hres, hkinds in variants:
+            assert [kind(a) for a in args] == hkinds, (name, [kind(a) for a in args], hkinds)
+            assert (res is None) == (hres == "void"), name
 
 
 def test_library_exports_every_declared_symbol():
