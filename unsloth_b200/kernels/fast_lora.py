@@ -17,6 +17,8 @@ algebra (fast_lora.py:42-62); what changes is how it is executed on a B200:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib as L
@@ -28,6 +30,22 @@ from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
                     geglu_approx_forward_kernel, geglu_approx_backward_kernel)
 
 _SM = 148
+
+# EXPERIMENTAL (default off; written after the round-1 GPU budget was spent, not yet run on
+# hardware): the rank-block GEMMs of a backward (dB_i = s dY_i^T XA, N = 64, 64-128 CTAs each) do
+# not depend on G / dA / dX, so they can run on a side stream next to the other skinny GEMMs and
+# fill the SMs those leave idle.  Fork/join with events, so it is capturable in the step's CUDA
+# graph (parallel branches).  UB200_SKINNY_STREAMS=1 turns it on.
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    if os.environ.get("UB200_SKINNY_STREAMS", "0") != "1":
+        return None
+    st = _SIDE_STREAMS.get(device.index)
+    if st is None:
+        st = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _epoch():
@@ -142,6 +160,26 @@ class _Group:
         grads = []
         G = None
         if self.has_lora:
+            side = _side_stream(dev)
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())       # fork: dYs / XA are ready here
+            # dB_i [out, Rp] = s_i * dY_i^T @ XA ; keep this adapter's columns.  Independent of G.
+            def _dBs():
+                res = []
+                for dY, (W, Wq, A, B, s) in zip(dYs, self.projs):
+                    if A is None:
+                        res.append(None)
+                        continue
+                    out_f = dY.shape[1]
+                    dB_full = torch.empty((out_f, Rp), dtype=torch.float32, device=dev)
+                    gemm(out_f, Rp, [(dY, XA, T)], dB_full, a_mn=True, b_mn=True, alpha=s,
+                         split_k=_split_k(out_f, Rp, T))
+                    res.append(dB_full)
+                return res
+            dB_fulls = None
+            if side is not None:
+                with torch.cuda.stream(side):
+                    dB_fulls = _dBs()
             # G[T, Rp] = sum_i dY_i @ (s_i B_i) placed at the adapter's rank slot.  The B operand
             # is the SAME zero-padded [out_i, Rp] block the forward used, consumed MN-major
             # ([K=out_i, N=Rp] row-major): no transposed copy of B is ever made.
@@ -158,16 +196,15 @@ class _Group:
             dA_catT = torch.empty((self.in_f, Rp), dtype=torch.float32, device=dev)
             gemm(self.in_f, Rp, [(X2, G, T)], dA_catT, a_mn=True, b_mn=True,
                  split_k=_split_k(self.in_f, Rp, T))
-            for off, dY, (W, Wq, A, B, s) in zip(self.offs, dYs, self.projs):
+            if dB_fulls is None:
+                dB_fulls = _dBs()
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+            for off, dY, dB_full, (W, Wq, A, B, s) in zip(self.offs, dYs, dB_fulls, self.projs):
                 if A is None:
                     grads.append((None, None))
                     continue
                 r = A.shape[0]
-                out_f = dY.shape[1]
-                # dB_i [out, Rp] = s_i * dY_i^T @ XA ; keep this adapter's columns
-                dB_full = torch.empty((out_f, Rp), dtype=torch.float32, device=dev)
-                gemm(out_f, Rp, [(dY, XA, T)], dB_full, a_mn=True, b_mn=True, alpha=s,
-                     split_k=_split_k(out_f, Rp, T))
                 grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
         else:
             grads = [(None, None)] * len(self.projs)
