@@ -44,7 +44,7 @@ def _reference_from(model, cfg):
                 if not hasattr(po, name):
                     continue
                 W, Wq, A, B, s = get_lora_parameters(getattr(po, name))
-                Wd = fast_dequantize(W, Wq).float().cpu()
+                Wd = fast_dequantize(W, Wq).float().cpu().clone()      # clone: leave inference mode
                 setattr(pr, name, PlainLoRA(Wd, A.detach().float().cpu().clone(), B.detach().float().cpu().clone(), s))
     for p_ in ref.parameters():
         p_.requires_grad_(False)

@@ -1,0 +1,327 @@
+"""HOST LOGIC of the shipped Python layer (kernels/*.py, patch.py) on a CPU-only box: every C-ABI
+call is interpreted by tests/abi_emulator.py (oracle arithmetic on the raw pointers / strides the
+shims pass), so what is exercised here is everything ABOVE the ABI -- views and strides handed to
+the kernels, in-place contracts, label shifting and item counts, chunking of the fused CE, the
+rank-block orchestration, the fused add+norm chain, packed batches, UNSLOTH_RETURN_LOGITS.
+References: the golden vectors produced by the reference's own kernels, and the stock HuggingFace
+model (the configs[0] reference path).  The GPU suite checks the same calls on the real library."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+import abi_emulator as EMU
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def close(a, b, rtol=1e-5, atol=1e-5):
+    torch.testing.assert_close(a.detach().float(), (b if torch.is_tensor(b) else T(b)).float(), rtol=rtol, atol=atol)
+
+
+class Norm:
+    def __init__(self, w, eps):
+        self.weight, self.variance_epsilon = w, eps
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    return EMU.install(monkeypatch)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel shims
+# ------------------------------------------------------------------------------------------------
+def test_rmsnorm_shim(golden, emu):
+    from unsloth_b200.kernels import fast_rms_layernorm
+    for name in ("rms_llama_512", "rms_llama_odd", "rms_gemma_256"):
+        g = golden(name)
+        X = T(g["X"]).clone().requires_grad_()
+        Y = fast_rms_layernorm(Norm(T(g["W"]), float(g["eps"])), X, gemma=bool(g["gemma"]))
+        close(Y, g["Y"])
+        dY = T(g["dY"]).clone()
+        Y.backward(dY)
+        close(X.grad, g["dX"], atol=2e-5)
+        if not bool(g["gemma"]):
+            assert X.grad.data_ptr() == dY.data_ptr()          # in place over dY (rms_layernorm.py:218)
+    assert set(emu) == {"ub200_rms_layernorm_fwd", "ub200_rms_layernorm_bwd"}
+
+
+def test_rope_shim_in_place_on_strided_views(golden, emu):
+    from unsloth_b200.kernels import fast_rope_embedding
+    g = golden("rope_noindex")
+    Q, K = T(g["Q"]), T(g["K"])
+    B, Hq, S, D = Q.shape
+    # the layout of the model: Q is a transposed VIEW of the [B, S, H*D] projection buffer
+    qbuf = Q.transpose(1, 2).reshape(B, S, Hq * D).clone()
+    kbuf = K.transpose(1, 2).reshape(B, S, K.shape[1] * D).clone()
+    Qv = qbuf.view(B, S, Hq, D).transpose(1, 2).requires_grad_()
+    Kv = kbuf.view(B, S, K.shape[1], D).transpose(1, 2).requires_grad_()
+    Qo, Ko = fast_rope_embedding(Qv, Kv, T(g["cos"]), T(g["sin"]))
+    close(Qo, g["Qo"]); close(Ko, g["Ko"])
+    assert Qo.data_ptr() == qbuf.data_ptr() and Ko.data_ptr() == kbuf.data_ptr()      # rotated in place, no copy
+    torch.autograd.backward([Qo, Ko], [T(g["dQ"]).clone(), T(g["dK"]).clone()])
+    close(Qv.grad, g["gQ"]); close(Kv.grad, g["gK"])
+    g = golden("rope_index")
+    Qv, Kv = T(g["Q"]).clone().requires_grad_(), T(g["K"]).clone().requires_grad_()
+    Qo, Ko = fast_rope_embedding(Qv, Kv, T(g["cos"]), T(g["sin"]), T(g["idx"]))
+    close(Qo, g["Qo"]); close(Ko, g["Ko"])
+    torch.autograd.backward([Qo, Ko], [T(g["dQ"]).clone(), T(g["dK"]).clone()])
+    close(Qv.grad, g["gQ"]); close(Kv.grad, g["gK"])
+    assert emu.count("ub200_rope_qk") == 4                      # Q and K in ONE launch per direction
+
+
+@pytest.mark.parametrize("name", ["ce_v1000", "ce_v70000_chunked", "ce_softcap30", "ce_scale"])
+def test_cross_entropy_shim(golden, emu, name):
+    from unsloth_b200.kernels import fast_cross_entropy_loss
+    g = golden(name)
+    logits = T(g["logits"]).clone().requires_grad_()
+    lg = logits * 1.0
+    loss = fast_cross_entropy_loss(lg, T(g["labels"]), float(g["softcap"]), float(g["scale"]))
+    close(loss, g["loss"])
+    loss.backward()
+    close(logits.grad, g["dlogits"], atol=1e-6)
+
+
+def test_glu_shims(golden, emu):
+    import unsloth_b200.kernels as K
+    for name, fwd, bwd in (("swiglu", K.swiglu_fg_kernel, K.swiglu_DWf_DW_dfg_kernel),
+                           ("geglu_approx", K.geglu_approx_forward_kernel, K.geglu_approx_backward_kernel),
+                           ("geglu_exact", K.geglu_exact_forward_kernel, K.geglu_exact_backward_kernel)):
+        g = golden(name)
+        e, up, DW = T(g["e"]), T(g["g"]), T(g["DW"]).clone()
+        close(fwd(e, up), g["h"])
+        e2, g2 = e.reshape(-1, e.shape[-1]).clone(), up.reshape(-1, up.shape[-1]).clone()
+        h, df, de = bwd(DW, e2, g2)
+        close(h, g["bh"]); close(df, g["bdf"]); close(de, g["bde"])
+        assert h.data_ptr() == DW.data_ptr() and df.data_ptr() == e2.data_ptr() and de.data_ptr() == g2.data_ptr()
+
+
+def test_nf4_quantise_dequantise_and_matmul_lora(emu):
+    from unsloth_b200.kernels import fast_dequantize, matmul_lora
+    from unsloth_b200.nf4 import quantize_nf4
+    torch.manual_seed(0)
+    W = torch.randn(96, 128) * 0.02
+    packed, qs = quantize_nf4(W)
+    packed_r, qs_r = R.quantize_nf4(W)
+    assert torch.equal(packed, packed_r) and torch.equal(qs.absmax, qs_r.absmax)
+    D = fast_dequantize(packed, qs)
+    assert torch.equal(D, R.dequantize_nf4(packed_r, qs_r))
+    assert fast_dequantize(packed.t(), qs).shape == (128, 96)            # transposed contract (utils.py:678)
+    assert fast_dequantize(W, None) is W
+    X = torch.randn(2, 5, 128)
+    A, B = torch.randn(8, 128) * 0.1, torch.randn(96, 8) * 0.1
+    out = matmul_lora(X, packed, qs, A, B, 0.5)
+    close(out, X @ D.t() + 0.5 * (X @ A.t()) @ B.t(), atol=1e-5)
+
+
+@pytest.mark.parametrize("softcap,n_items", [(0.0, None), (30.0, 13), (0.0, 7)])
+def test_fused_ce_host_logic(emu, softcap, n_items):
+    """Chunking, internal label shift, n_items and the gradient wrt the hidden states of the
+    logits-free loss against the oracle's `hidden @ W.T -> shift -> CE` (llama.py:1525-1562)."""
+    from unsloth_b200.kernels import unsloth_fused_ce_loss
+    torch.manual_seed(1)
+    Bz, S, H, V = 2, 100, 32, 211            # T = 200 rows -> two 128-row chunks
+    hidden = torch.randn(Bz, S, H, requires_grad=True)
+    Wt = torch.randn(V, H) * 0.2
+    labels = torch.randint(0, V, (Bz, S)); labels[0, 3] = -100; labels[1, 0] = -100
+    ref = R.fused_linear_cross_entropy(hidden.detach(), Wt, labels, n_items=n_items, softcap=softcap)
+    loss = unsloth_fused_ce_loss(trainer=None, hidden_states=hidden, lm_head_weight=Wt, lm_head_bias=None,
+                                 labels=labels, mask=None, n_items=n_items, scaling=None, target_gb=None,
+                                 torch_compile=False, logit_softcapping=softcap, chunk_rows=128)
+    close(loss, ref[0], atol=2e-5)
+    loss.backward()
+    close(hidden.grad, ref[1], atol=2e-5)
+    h2 = hidden.detach().clone().requires_grad_()
+    logits = h2 @ Wt.t()
+    if softcap:
+        logits = softcap * torch.tanh(logits / softcap)
+    shift = torch.full_like(labels, -100); shift[:, :-1] = labels[:, 1:]
+    den = n_items if n_items is not None else (shift != -100).sum()
+    (torch.nn.functional.cross_entropy(logits.view(-1, V), shift.view(-1), ignore_index=-100, reduction="sum") / den).backward()
+    close(hidden.grad, h2.grad, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole model: patch.install + fast forwards, against stock HuggingFace (the configs[0] reference)
+# ------------------------------------------------------------------------------------------------
+TINY = dict(hidden_size=64, intermediate_size=128, num_attention_heads=4, num_key_value_heads=2,
+            head_dim=16, vocab_size=256)
+
+
+def attention_double(Q, K_, V, scale, window, softcap, seq_info=None):
+    """The external attention call ([B,S,H,D] in, [B,S,Hq,D] out) in plain torch: causal, optional
+    sliding window / soft cap, block-diagonal per document when `seq_info` is given."""
+    B, S, Hq, D = Q.shape
+    rep = Hq // K_.shape[2]
+    q, k, v = (t.float() for t in (Q, K_, V))
+    if seq_info is not None:
+        q, k, v = (t.reshape(1, B * S, t.shape[2], D) for t in (q, k, v))
+    n = q.shape[1]
+    q, k, v = q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3).repeat_interleave(rep, 1), v.permute(0, 2, 1, 3).repeat_interleave(rep, 1)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if softcap:
+        s = softcap * torch.tanh(s / softcap)
+    i, j = torch.arange(n)[:, None], torch.arange(n)[None, :]
+    mask = j <= i
+    if window != (-1, -1):
+        mask = mask & (j >= i - window[0])
+    if seq_info is not None:
+        doc = torch.repeat_interleave(torch.arange(seq_info[0].numel()), seq_info[0].long())
+        mask = mask & (doc[:, None] == doc[None, :])
+    o = torch.softmax(s.masked_fill(~mask, float("-inf")), -1) @ v
+    return o.permute(0, 2, 1, 3).reshape(B, S, Hq, D).to(Q.dtype)
+
+
+@pytest.fixture
+def cpu_model(emu, monkeypatch):
+    import unsloth_b200.patch as P
+    from unsloth_b200.kernels import utils as KU
+    monkeypatch.setattr(P, "_attention", attention_double)
+    KU.set_keep_dequant(False)
+    yield P
+    KU.set_keep_dequant(None)
+    P.FUSE_ADD_NORM = True
+
+
+def _build(P, name, dtype=torch.float32, layers=2, **extra):
+    return P.build_qlora_model(name, r=4, lora_alpha=8, device="cpu", dtype=dtype, num_hidden_layers=layers,
+                               init_b_std=0.05, **dict(TINY, **extra))
+
+
+def _grads(P, model):
+    return torch.cat([p.grad.float().flatten() for p in P.lora_parameters(model)])
+
+
+def _zero(P, model):
+    for p in P.lora_parameters(model):
+        p.grad = None
+
+
+@pytest.mark.parametrize("name,extra,seq", [("llama-3-8b", {}, 24), ("llama-3.2-1b", {}, 20),
+                                            ("mistral-7b-v0.3", {"sliding_window": 8}, 24),
+                                            ("gemma-2-9b", {"query_pre_attn_scalar": 16, "sliding_window": 8}, 20)])
+def test_patched_model_matches_stock_hf_on_cpu(cpu_model, name, extra, seq):
+    """fp32 end to end: NF4 weights dequantised into a stock HF model with plain LoRA (the reference
+    CPU path) must give the same loss and the same LoRA gradients as the patched model."""
+    from test_gpu_model import _reference_from
+    P = cpu_model
+    model = _build(P, name, **extra)
+    ref_extra = dict(extra)
+    if "sliding_window" in ref_extra:
+        # the reference hands flash-attn window_size = (sw, sw) (mistral.py:112-128, gemma2.py:139-150):
+        # key j is visible iff j >= i - sw, i.e. sw + 1 keys; HF's own mask keeps i - j < sliding_window
+        ref_extra["sliding_window"] += 1
+    cfg = P.hf_config(name, 2, **dict(TINY, **ref_extra))
+    ref = _reference_from(model, cfg)
+    torch.manual_seed(1)
+    ids = torch.randint(0, TINY["vocab_size"], (2, seq))
+    labels = ids.clone(); labels[0, :3] = -100
+    out = model(input_ids=ids, labels=labels)
+    out.loss.backward()
+    ref_out = ref(input_ids=ids, labels=labels)
+    ref_out.loss.backward()
+    assert abs(out.loss.item() - ref_out.loss.item()) <= 2e-4 * abs(ref_out.loss.item())
+    from unsloth_b200.kernels import get_lora_parameters
+    for lo, lr in zip(model.model.layers, ref.model.layers):
+        for po, pr in ((lo.self_attn, lr.self_attn), (lo.mlp, lr.mlp)):
+            for pn in P.TARGET_MODULES:
+                if not hasattr(po, pn):
+                    continue
+                _, _, A, B, _ = get_lora_parameters(getattr(po, pn))
+                close(A.grad, getattr(pr, pn).A.grad, rtol=2e-3, atol=2e-6)
+                close(B.grad, getattr(pr, pn).B.grad, rtol=2e-3, atol=2e-6)
+
+
+def test_fused_add_norm_chain_on_cpu(cpu_model):
+    """bf16: the (residual, normed) chain of fast_add_rms_layernorm against the layer-by-layer form:
+    identical forward, gradients equal up to the one rounding the fusion removes."""
+    P = cpu_model
+    model = _build(P, "llama-3-8b", dtype=torch.bfloat16, layers=3)
+    torch.manual_seed(2)
+    ids = torch.randint(0, TINY["vocab_size"], (2, 16))
+    res = {}
+    for fuse in (True, False):
+        P.FUSE_ADD_NORM = fuse
+        _zero(P, model)
+        loss = model(input_ids=ids, labels=ids).loss
+        loss.backward()
+        res[fuse] = (loss.item(), _grads(P, model))
+    assert res[True][0] == res[False][0]
+    a, b = res[True][1], res[False][1]
+    assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.999
+
+
+def test_packed_row_on_cpu(cpu_model):
+    P = cpu_model
+    model = _build(P, "mistral-7b-v0.3", sliding_window=6)
+    torch.manual_seed(3)
+    L1, L2 = 9, 14
+    d1 = torch.randint(0, TINY["vocab_size"], (1, L1)); d2 = torch.randint(0, TINY["vocab_size"], (1, L2))
+    row = torch.cat([d1, d2], 1)
+    lens = torch.tensor([L1, L2], dtype=torch.int32)
+    with torch.no_grad():
+        hp = model(input_ids=row, packed_seq_lengths=lens).hidden_states
+        h1, h2 = model(input_ids=d1).hidden_states, model(input_ids=d2).hidden_states
+        leaked = model(input_ids=row).hidden_states
+    close(hp[:, :L1], h1, rtol=1e-4, atol=1e-5); close(hp[:, L1:], h2, rtol=1e-4, atol=1e-5)
+    assert (leaked[:, L1:] - h2).abs().max() > 1e-2 * h2.abs().max()
+    n = L1 + L2 - 2
+    _zero(P, model)
+    lp = model(input_ids=row, labels=row, packed_seq_lengths=lens, num_items_in_batch=n).loss
+    lp.backward()
+    gp = _grads(P, model)
+    _zero(P, model)
+    ls = 0.0
+    for d in (d1, d2):
+        l = model(input_ids=d, labels=d, num_items_in_batch=n).loss
+        l.backward()
+        ls += l.item()
+    assert abs(lp.item() - ls) <= 1e-4 * abs(ls)
+    close(gp, _grads(P, model), rtol=2e-3, atol=1e-6)
+    from unsloth_b200.packing import num_items_in_batch
+    assert num_items_in_batch(row, lens) == n
+
+
+def test_return_logits_path_on_cpu(cpu_model, monkeypatch):
+    """UNSLOTH_RETURN_LOGITS=1 (llama.py:1525-1562) == the logits-free default, incl. packed rows."""
+    P = cpu_model
+    for name, extra in (("llama-3-8b", {}), ("gemma-2-9b", {"query_pre_attn_scalar": 16})):
+        model = _build(P, name, **extra)
+        torch.manual_seed(4)
+        ids = torch.randint(0, TINY["vocab_size"], (1, 18))
+        labels = ids.clone(); labels[0, :4] = -100
+        lens = torch.tensor([7, 11], dtype=torch.int32)
+        res = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("UNSLOTH_RETURN_LOGITS", flag)
+            _zero(P, model)
+            out = model(input_ids=ids, labels=labels, packed_seq_lengths=lens)
+            out.loss.backward()
+            res[flag] = (out.loss.item(), _grads(P, model), out.logits)
+        assert res["0"][2] is None and res["1"][2].shape == (1, 18, TINY["vocab_size"])
+        assert abs(res["0"][0] - res["1"][0]) <= 1e-5 * abs(res["0"][0])
+        close(res["1"][1], res["0"][1], rtol=1e-3, atol=1e-6)
+
+
+def test_keep_dequant_on_cpu(cpu_model):
+    from unsloth_b200.kernels import utils as KU
+    P = cpu_model
+    model = _build(P, "llama-3-8b")
+    ids = torch.randint(0, TINY["vocab_size"], (2, 12), generator=torch.Generator().manual_seed(5))
+    res = {}
+    import unsloth_b200._lib as L
+    for keep in (True, False):
+        KU.set_keep_dequant(keep)
+        KU.bump_param_epoch()
+        _zero(P, model)
+        n0 = L.launch_count
+        loss = model(input_ids=ids, labels=ids).loss
+        loss.backward()
+        res[keep] = (loss.item(), _grads(P, model), L.launch_count - n0)
+    assert res[True][0] == res[False][0] and torch.equal(res[True][1], res[False][1])
+    assert res[False][2] - res[True][2] == 2 * 7 - 3        # q/k/v of layer 0 form no dX
