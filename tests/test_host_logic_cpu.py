@@ -325,3 +325,51 @@ def test_keep_dequant_on_cpu(cpu_model):
         res[keep] = (loss.item(), _grads(P, model), L.launch_count - n0)
     assert res[True][0] == res[False][0] and torch.equal(res[True][1], res[False][1])
     assert res[False][2] - res[True][2] == 2 * 7 - 3        # q/k/v of layer 0 form no dX
+
+
+def test_decode_path_host_logic(emu):
+    """fast_gemv / fast_linear_forward (kernels/utils.py:874-973, :1082-1125) and merge_lora
+    (save.py:620-646): branch selection, LoRA temp, epilogue arguments, bias, `out=` reuse."""
+    from unsloth_b200.kernels import fast_gemv, fast_linear_forward, fast_dequantize, get_lora_parameters
+    from unsloth_b200.lora import LoraLinear
+    from unsloth_b200.nf4 import Linear4bit
+    from unsloth_b200.save import merge_lora
+    torch.manual_seed(8)
+    k, m = 128, 96
+    W = (torch.randn(m, k) * 0.05).to(torch.bfloat16)
+    proj = LoraLinear(Linear4bit.from_dense(W), r=8, lora_alpha=16, init_b_std=0.1)
+    Wq, qs, A, B, s = get_lora_parameters(proj)
+    Wd = fast_dequantize(Wq, qs).float()
+    full = Wd + s * (B.float() @ A.float())
+    x = torch.randn(1, 1, k).to(torch.bfloat16)
+    emu.clear()
+    y = fast_gemv(x, Wq, qs)
+    assert emu == ["ub200_gemv_nf4"] and y.shape == (1, 1, m)                       # ONE launch
+    close(y.view(-1), Wd @ x.view(-1).float(), rtol=2e-2, atol=2e-2)
+    out = torch.empty(1, 1, m, dtype=torch.bfloat16)
+    assert fast_gemv(x, Wq, qs, out=out).data_ptr() == out.data_ptr()
+    emu.clear()
+    y1 = fast_linear_forward(proj, x)
+    assert emu == ["ub200_gemv_dense", "ub200_gemv_nf4"]                            # A x, then GEMV + epilogue
+    close(y1.view(-1), full @ x.view(-1).float(), rtol=2e-2, atol=3e-2)
+    ref = R.fast_linear_forward(x, Wq, qs, A.detach(), B.detach(), s)
+    close(y1.view(-1), ref, rtol=8e-3, atol=8e-3)
+    # q_len != 1 falls through to the training primitive; bsz > 1 uses the GEMM on [bsz, in] rows
+    x3 = torch.randn(1, 3, k).to(torch.bfloat16)
+    close(fast_linear_forward(proj, x3).view(3, m), x3.view(3, k).float() @ full.t(), rtol=2e-2, atol=3e-2)
+    x4 = torch.randn(4, 1, k).to(torch.bfloat16)
+    y4 = fast_linear_forward(proj, x4)
+    assert y4.shape == (4, 1, m)
+    close(y4.view(4, m), x4.view(4, k).float() @ full.t(), rtol=2e-2, atol=3e-2)
+    # dense 16-bit base with a bias
+    base = torch.nn.Linear(k, m, bias=True, dtype=torch.bfloat16)
+    dense = LoraLinear(base, r=8, lora_alpha=16, init_b_std=0.1)
+    Wn, _, A2, B2, s2 = get_lora_parameters(dense)
+    yd = fast_linear_forward(dense, x)
+    close(yd.view(-1), (Wn.float() + s2 * (B2.float() @ A2.float())) @ x.view(-1).float() + base.bias.float(),
+          rtol=2e-2, atol=3e-2)
+    # merge: W + s B A formed in fp32, rounded once
+    Wm, bias = merge_lora(proj, "proj")
+    assert bias is None and torch.equal(Wm, full.to(torch.bfloat16))
+    proj.disable_adapters = True
+    assert torch.equal(merge_lora(proj)[0], Wd.to(torch.bfloat16))
