@@ -373,3 +373,30 @@ def test_decode_path_host_logic(emu):
     assert bias is None and torch.equal(Wm, full.to(torch.bfloat16))
     proj.disable_adapters = True
     assert torch.equal(merge_lora(proj)[0], Wd.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("name,dtype,fuse,packed", [
+    ("llama-3-8b", torch.bfloat16, True, False), ("llama-3-8b", torch.float32, False, False),
+    ("gemma-2-9b", torch.float32, True, False), ("mistral-7b-v0.3", torch.bfloat16, True, True)])
+def test_gradient_checkpointing_recompute_is_exact(cpu_model, name, dtype, fuse, packed):
+    """Per-layer recompute in the backward (install(..., gradient_checkpointing=True)) must give the
+    same loss and bit-identical LoRA gradients: the in-place kernels (RoPE on the projection
+    buffers, dX into the saved X, dY -> dX of RMSNorm, the residual-gradient accumulation) have to
+    survive the second forward.  The emulator reproduces the in-place memory semantics."""
+    P = cpu_model
+    extra = {"query_pre_attn_scalar": 16} if name.startswith("gemma") else {}
+    model = _build(P, name, dtype=dtype, layers=3, **extra)
+    P.FUSE_ADD_NORM = fuse
+    torch.manual_seed(6)
+    ids = torch.randint(0, TINY["vocab_size"], (1 if packed else 2, 20))
+    kw = dict(packed_seq_lengths=torch.tensor([8, 12], dtype=torch.int32)) if packed else {}
+    res = {}
+    for ck in (False, True):
+        model.model._ub_gradient_checkpointing = ck
+        _zero(P, model)
+        loss = model(input_ids=ids, labels=ids, **kw).loss
+        loss.backward()
+        res[ck] = (loss.item(), _grads(P, model))
+    assert res[True][0] == res[False][0]
+    assert torch.equal(res[True][1], res[False][1])
+    assert res[True][1].abs().max() > 0

@@ -197,9 +197,19 @@ def Model_fast_forward(self, input_ids, position_ids=None, packed_seq_lengths=No
     idx = None
     if position_ids is not None:
         idx = position_ids.reshape(-1).to(torch.int32)
+    # optional recompute of every decoder layer in the backward (the plain-recompute part of the
+    # reference's use_gradient_checkpointing, models/llama.py:1169-1192; no activation offload):
+    # not needed for the BASELINE configs on a 180 GB B200, available for longer sequences
+    ckpt = getattr(self, "_ub_gradient_checkpointing", False) and torch.is_grad_enabled()
+    if ckpt:
+        from torch.utils.checkpoint import checkpoint
     if self._ub_gemma or not FUSE_ADD_NORM:
         for layer in self.layers:
-            h = DecoderLayer_fast_forward(layer, h, cos, sin, idx, seq_info)
+            if ckpt:
+                h = checkpoint(DecoderLayer_fast_forward, layer, h, cos, sin, idx, seq_info,
+                               use_reentrant=False, preserve_rng_state=False)
+            else:
+                h = DecoderLayer_fast_forward(layer, h, cos, sin, idx, seq_info)
         return K.fast_rms_layernorm(self.norm, h, gemma=self._ub_gemma)
     # Llama / Mistral: every `residual + branch` is fused with the norm that consumes the sum
     # (this layer's post_attention_layernorm, then the NEXT layer's input_layernorm or the final
@@ -207,12 +217,20 @@ def Model_fast_forward(self, input_ids, position_ids=None, packed_seq_lengths=No
     layers = list(self.layers)
     residual = h
     normed = K.fast_rms_layernorm(layers[0].input_layernorm, h)
-    for i, layer in enumerate(layers):
+    def layer_step(i, residual, normed):
+        layer = layers[i]
         a = LlamaAttention_fast_forward(layer.self_attn, normed, cos, sin, idx, seq_info)
         residual, normed = K.fast_add_rms_layernorm(layer.post_attention_layernorm, residual, a)
         m = layer.mlp(normed)
         nxt = layers[i + 1].input_layernorm if i + 1 < len(layers) else self.norm
-        residual, normed = K.fast_add_rms_layernorm(nxt, residual, m)
+        return K.fast_add_rms_layernorm(nxt, residual, m)
+
+    for i in range(len(layers)):
+        if ckpt:
+            residual, normed = checkpoint(layer_step, i, residual, normed, use_reentrant=False,
+                                          preserve_rng_state=False)
+        else:
+            residual, normed = layer_step(i, residual, normed)
     return normed
 
 
@@ -255,9 +273,10 @@ def _arch_of(model):
     return mt
 
 
-def install(model):
+def install(model, gradient_checkpointing=False):
     """Rebind a HuggingFace Llama / Mistral / Gemma-2 CausalLM (with LoRA-wrapped projections)
-    onto the unsloth_b200 kernels.  Returns the model."""
+    onto the unsloth_b200 kernels.  Returns the model.  `gradient_checkpointing`: recompute each
+    decoder layer in the backward (off by default: the BASELINE configs fit a B200 without)."""
     arch = _arch_of(model)
     cfg = model.config
     gemma = arch == "gemma2"
@@ -275,6 +294,7 @@ def install(model):
     inner._ub_rotary = RotaryCache(hd, float(rope_theta or 10000.0), dev,
                                    torch.float32 if gemma else dtype, rope_scaling)
     inner._ub_gemma = gemma
+    inner._ub_gradient_checkpointing = bool(gradient_checkpointing)
     model._ub_final_softcap = float(getattr(cfg, "final_logit_softcapping", 0) or 0)
     mlp_fn = K.apply_lora_mlp_geglu_approx if gemma else K.apply_lora_mlp_swiglu   # llama.py:3618-3639
     for i, layer in enumerate(inner.layers):
@@ -346,7 +366,8 @@ def hf_config(name, num_hidden_layers=None, **overrides):
 
 
 def build_qlora_model(name="llama-3-8b", r=16, lora_alpha=16, device="cuda", dtype=torch.bfloat16,
-                      seed=3407, init_b_std=0.0, num_hidden_layers=None, quantize=True, **overrides):
+                      seed=3407, init_b_std=0.0, num_hidden_layers=None, quantize=True,
+                      gradient_checkpointing=False, **overrides):
     """Random-init model of a BASELINE.json config on `device`, NF4 + LoRA, kernels installed."""
     from transformers import AutoModelForCausalLM
     cfg = hf_config(name, num_hidden_layers, **overrides)
@@ -361,4 +382,4 @@ def build_qlora_model(name="llama-3-8b", r=16, lora_alpha=16, device="cuda", dty
     model.to(dtype)
     attach_qlora(model, r=r, lora_alpha=lora_alpha, init_b_std=init_b_std, quantize=quantize)
     torch.cuda.empty_cache()
-    return install(model)
+    return install(model, gradient_checkpointing=gradient_checkpointing)
