@@ -83,7 +83,8 @@ def test_python_surface_matches_reference_names():
                  "LoRA_QKV", "LoRA_W", "swiglu_fg_kernel", "swiglu_DWf_DW_dfg_kernel",
                  "geglu_approx_forward_kernel", "geglu_approx_backward_kernel",
                  "Fast_RMS_Layernorm", "Fast_RoPE_Embedding", "Fast_RoPE_Embedding_QK",
-                 "Fast_CrossEntropyLoss", "patch_rms_layernorm"):
+                 "Fast_CrossEntropyLoss", "patch_rms_layernorm", "patch_loss_functions",
+                 "fast_gemv", "fast_linear_forward", "fast_add_rms_layernorm"):
         assert hasattr(K, name), name
 
 

@@ -400,3 +400,37 @@ def test_gradient_checkpointing_recompute_is_exact(cpu_model, name, dtype, fuse,
     assert res[True][0] == res[False][0]
     assert torch.equal(res[True][1], res[False][1])
     assert res[True][1].abs().max() > 0
+
+
+def test_class_level_routes_serve_a_stock_hf_model(emu):
+    """SURVEY 8b, class-level alternative: `patch_rms_layernorm` (rms_layernorm.py:261-274) and
+    `patch_loss_functions` (cross_entropy_loss.py:459-473) let the kernels serve a STOCK HF Llama
+    (no fast forwards): same loss and gradients as the unpatched model."""
+    import unsloth_b200.kernels as K
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_attention_heads=4, num_key_value_heads=2,
+                      num_hidden_layers=2, vocab_size=256, max_position_embeddings=64)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    ids = torch.randint(0, 256, (2, 14))
+    labels = ids.clone(); labels[0, :4] = -100
+    base = LlamaForCausalLM(cfg).float()
+    sd = copy.deepcopy(base.state_dict())
+    out0 = base(input_ids=ids, labels=labels)
+    out0.loss.backward()
+    g0 = base.model.layers[0].mlp.down_proj.weight.grad.clone()
+    K.patch_rms_layernorm(); K.patch_loss_functions()
+    try:
+        patched = LlamaForCausalLM(cfg).float()              # built AFTER the class swap
+        patched.load_state_dict(sd)
+        emu.clear()
+        out1 = patched(input_ids=ids, labels=labels)
+        out1.loss.backward()
+        assert "ub200_rms_layernorm_fwd" in emu and "ub200_cross_entropy_fwd" in emu
+        assert "ub200_rms_layernorm_bwd" in emu and "ub200_cross_entropy_bwd" in emu
+    finally:
+        K.unpatch_rms_layernorm(); K.unpatch_loss_functions()
+    close(out1.loss, out0.loss, rtol=1e-5, atol=1e-6)
+    close(patched.model.layers[0].mlp.down_proj.weight.grad, g0, rtol=1e-4, atol=1e-7)
+    import transformers.loss.loss_utils as lu
+    assert lu.LOSS_MAPPING["ForCausalLM"].__name__ == "ForCausalLMLoss"             # restored

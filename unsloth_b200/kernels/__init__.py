@@ -1,6 +1,7 @@
 """Kernel API of unsloth_b200: the same names `unsloth/kernels/__init__.py:15-62` exports."""
 from .cross_entropy_loss import (fast_cross_entropy_loss, Fast_CrossEntropyLoss,
-                                 unsloth_fused_ce_loss, MAX_FUSED_SIZE)
+                                 unsloth_fused_ce_loss, MAX_FUSED_SIZE, patch_loss_functions,
+                                 unpatch_loss_functions, UnslothForCausalLMLoss)
 from .rms_layernorm import (fast_rms_layernorm, Fast_RMS_Layernorm, patch_rms_layernorm,
                             unpatch_rms_layernorm, fast_add_rms_layernorm, Fast_Add_RMS_Layernorm)
 from .rope_embedding import fast_rope_embedding, Fast_RoPE_Embedding, Fast_RoPE_Embedding_QK

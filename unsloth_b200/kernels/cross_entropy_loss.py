@@ -137,3 +137,43 @@ def unsloth_fused_ce_loss(trainer=None, hidden_states=None, lm_head_weight=None,
     return Fused_Linear_CrossEntropy.apply(h2, lm_head_weight, shift, inv_n,
                                            float(logit_softcapping or 0), float(scaling or 0),
                                            int(chunk_rows))
+
+
+# ---------------------------------------------------------------------------------------------
+# class-level route (cross_entropy_loss.py:459-473): serve a STOCK HuggingFace model
+# ---------------------------------------------------------------------------------------------
+_HF_LOSS_BACKUP = {}
+
+
+def UnslothForCausalLMLoss(logits, labels, vocab_size=None, num_items_in_batch=None, ignore_index=-100,
+                           shift_labels=None, **kwargs):
+    """Drop-in for transformers.loss.loss_utils.ForCausalLMLoss on materialised logits: same label
+    shift, then `fast_cross_entropy_loss` (no fp32 upcast copy of the logits; the gradient is
+    written in place into them)."""
+    if ignore_index != -100:
+        raise NotImplementedError("unsloth_b200: the CE kernels use ignore_index = -100")
+    if shift_labels is None:
+        labels = torch.nn.functional.pad(labels, (0, 1), value=-100)
+        shift_labels = labels[..., 1:].contiguous()
+    if logits.dim() == 2:
+        logits = logits.unsqueeze(0)
+    shift_labels = shift_labels.reshape(logits.shape[0], logits.shape[1]).to(logits.device)
+    return fast_cross_entropy_loss(logits, shift_labels, n_items=num_items_in_batch)
+
+
+def patch_loss_functions(torch_compile=False):
+    """cross_entropy_loss.py:459-473: point HF's LOSS_MAPPING["ForCausalLM"] (and the aliases that
+    still hold the stock function) at the kernel-backed loss.  `torch_compile` is accepted and
+    ignored: nothing here goes through a tracing compiler."""
+    import transformers.loss.loss_utils as lu
+    for key, fn in list(lu.LOSS_MAPPING.items()):
+        if getattr(fn, "__name__", "") == "ForCausalLMLoss":
+            _HF_LOSS_BACKUP.setdefault(key, fn)
+            lu.LOSS_MAPPING[key] = UnslothForCausalLMLoss
+
+
+def unpatch_loss_functions():
+    import transformers.loss.loss_utils as lu
+    for key, fn in _HF_LOSS_BACKUP.items():
+        lu.LOSS_MAPPING[key] = fn
+    _HF_LOSS_BACKUP.clear()
