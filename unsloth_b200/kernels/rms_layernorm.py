@@ -113,11 +113,12 @@ class Fast_Add_RMS_Layernorm(torch.autograd.Function):
 def fast_add_rms_layernorm(layernorm, residual: torch.Tensor, X: torch.Tensor):
     """`residual + X` followed by fast_rms_layernorm (models/llama.py:838-844), fused.  Returns
     (new_residual, normed).  Falls back to the two separate ops for fp32 activations, mixed
-    weight dtype or a hidden size that is not a multiple of 8 (the fused kernel is 16-bit packed)."""
+    weight dtype, a hidden size that is not a multiple of 8 or above 8192 (16-bit packed kernel,
+    at most four 16-byte vectors per thread)."""
     W = layernorm.weight
     eps = layernorm.variance_epsilon if hasattr(layernorm, "variance_epsilon") else layernorm.eps
     if (X.dtype in (torch.bfloat16, torch.float16) and W.dtype == X.dtype and residual.dtype == X.dtype
-            and X.shape[-1] % 8 == 0 and X.shape[-1] <= 16384):
+            and X.shape[-1] % 8 == 0 and X.shape[-1] <= 8192):    # wider rows: the 8-vector variant spills
         return Fast_Add_RMS_Layernorm.apply(residual, X, W, eps)
     S = residual + X
     return S, Fast_RMS_Layernorm.apply(S, W, eps, False)
