@@ -13,10 +13,13 @@ Parity pinning status
   * RMSNorm / RoPE / SwiGLU / GEGLU / CE / LoRA_MLP / LoRA_QKV / LoRA_W: pinned against
     the reference's own Triton kernels executed under TRITON_INTERPRET=1 (fp32) through
     oracle/ref_shim.py; the outputs are committed as tests/golden/*.npz by
-    oracle/make_golden.py and re-checked in tests/test_oracle_golden.py.
+    oracle/make_golden.py and re-checked in tests/test_oracle_golden.py.  The 16-bit ROUNDING
+    POINTS are pinned too: fp16 runs of the same reference kernels and
+    LoRA functions (tests/golden/fp16_*.npz) are reproduced to the ulp (LoRA: bit for bit).
   * NF4 double-quant dequantisation (bitsandbytes >=0.45.5, not vendored, not installed):
     restated from its published algorithm and the reference call site
-    kernels/utils.py:582-598, 650-675.  **parity unpinned**.
+    kernels/utils.py:582-598, 650-675; likewise the 4-bit GEMV of `fast_gemv` (:874-973).
+    **parity unpinned**.
   * Logits-free fused linear cross-entropy (unsloth_zoo >= 2026.8.13, not vendored, not
     installed): semantics restated from the logits path it replaces
     (models/llama.py:1525-1562 + kernels/cross_entropy_loss.py:421-449).
