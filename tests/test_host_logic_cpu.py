@@ -434,3 +434,68 @@ def test_class_level_routes_serve_a_stock_hf_model(emu):
     close(patched.model.layers[0].mlp.down_proj.weight.grad, g0, rtol=1e-4, atol=1e-7)
     import transformers.loss.loss_utils as lu
     assert lu.LOSS_MAPPING["ForCausalLM"].__name__ == "ForCausalLMLoss"             # restored
+
+
+def test_rope_promotion_and_single_tensor_forms(emu):
+    """Gemma-style fp32 tables with 16-bit Q/K: the no-index form computes in the TABLE dtype
+    (rope_embedding.py:154), so fp32 tables give fp32 products and one final rounding;
+    `Fast_RoPE_Embedding` (single [B,S,H,D] tensor, :169-261) shares the kernel, in place."""
+    from unsloth_b200.kernels import fast_rope_embedding, Fast_RoPE_Embedding
+    torch.manual_seed(0)
+    B, H, S, D = 2, 3, 7, 16
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+    fr = torch.outer(torch.arange(16).float(), inv)
+    cos, sin = torch.cat([fr, fr], -1).cos(), torch.cat([fr, fr], -1).sin()
+    Q = torch.randn(B, H, S, D).to(torch.bfloat16); K = torch.randn(B, 1, S, D).to(torch.bfloat16)
+    Qo, Ko = fast_rope_embedding(Q.clone(), K.clone(), cos, sin)
+    ref = R.rope_noindex(Q.transpose(1, 2), cos, sin).transpose(1, 2)
+    assert Qo.dtype == torch.bfloat16 and torch.equal(Qo, ref.to(torch.bfloat16))
+    # position ids == arange must reproduce the no-index result when everything is fp32
+    Qf, Kf = Q.float(), K.float()
+    a, _ = fast_rope_embedding(Qf.clone(), Kf.clone(), cos, sin)
+    b, _ = fast_rope_embedding(Qf.clone(), Kf.clone(), cos, sin, torch.arange(S).repeat(B))
+    close(a, b)
+    # single-tensor API on [B, S, H, D]
+    X0 = torch.randn(B, S, H, D)
+    X = X0.clone().requires_grad_()
+    Y = Fast_RoPE_Embedding.apply(X, cos, sin)                  # rotates X's storage in place
+    close(Y, R.rope_noindex(X0, cos, sin))
+    assert Y.data_ptr() == X.data_ptr()
+    Y.backward(torch.ones_like(Y))
+    close(X.grad, R.rope_noindex(torch.ones(B, S, H, D), cos, sin, backward=True))
+
+
+def test_cross_entropy_argument_forms(emu):
+    """`n_items` as int / tensor / None, `logit_scaling`, all-ignored rows (loss 0, zero gradient)."""
+    from unsloth_b200.kernels import fast_cross_entropy_loss
+    torch.manual_seed(3)
+    logits = torch.randn(2, 5, 50)
+    labels = torch.randint(0, 50, (2, 5)); labels[0] = -100
+    for n_items in (None, 5, torch.tensor(5)):
+        lg = logits.clone().requires_grad_()
+        loss = fast_cross_entropy_loss(lg * 1.0, labels, 0, 0.5, n_items=n_items)
+        ref = torch.nn.functional.cross_entropy((0.5 * logits).view(-1, 50), labels.view(-1), ignore_index=-100,
+                                                reduction="sum") / 5
+        close(loss, ref)
+        loss.backward()
+        assert lg.grad[0].abs().max() == 0
+    lg = logits.clone().requires_grad_()
+    all_ignored = torch.full((2, 5), -100)
+    loss = fast_cross_entropy_loss(lg * 1.0, all_ignored, n_items=1)
+    assert loss.item() == 0
+    loss.backward()
+    assert lg.grad.abs().max() == 0
+
+
+def test_fp16_model_runs_through_the_16bit_paths(cpu_model):
+    """fp16 end to end (the reference's T4 CI dtype): fused add+norm, packed RoPE tables in fp16,
+    loss finite and close to the fp32 model built from the same seed."""
+    P = cpu_model
+    m16 = _build(P, "llama-3-8b", dtype=torch.float16)
+    m32 = _build(P, "llama-3-8b", dtype=torch.float32)
+    ids = torch.randint(0, TINY["vocab_size"], (2, 16), generator=torch.Generator().manual_seed(1))
+    l16 = m16(input_ids=ids, labels=ids).loss
+    l32 = m32(input_ids=ids, labels=ids).loss
+    l16.backward()
+    assert torch.isfinite(l16) and abs(l16.item() - l32.item()) < 2e-2 * abs(l32.item())
+    assert all(torch.isfinite(p.grad).all() for p in P.lora_parameters(m16))
