@@ -12,23 +12,24 @@ from .kernels.utils import fast_dequantize, get_lora_parameters_bias
 
 @torch.inference_mode
 def merge_lora(layer, name: str = ""):
-    """Returns (W_merged [out, in] in the weight's 16-bit dtype, bias).  W + s * B @ A is formed in
-    fp32 on the transposed view, then rounded once (save.py:629-645); non-finite results raise."""
-    if not hasattr(layer, "base_layer") and not hasattr(getattr(layer, "weight", None), "quant_state"):
+    """Returns (W_merged [out, in] in the weight's 16-bit dtype, bias).  Same arithmetic as the
+    reference's `_merge_lora` (save.py:629-645): the update s * B @ A is added to the dequantised
+    weight in fp32 and the sum is rounded ONCE to the storage dtype; a non-finite result raises."""
+    wrapped = hasattr(layer, "base_layer") or hasattr(getattr(layer, "weight", None), "quant_state")
+    if not wrapped:
         return layer.weight, getattr(layer, "bias", None)
     W, quant_state, A, B, s, bias = get_lora_parameters_bias(layer)
-    if quant_state is not None:
-        dtype = quant_state.dtype if type(quant_state) is not list else quant_state[2]
-        W = fast_dequantize(W, quant_state)
+    if quant_state is None:
+        out_dtype, dense = W.dtype, W
     else:
-        dtype = W.dtype
-    W = W.to(torch.float32).t()
+        out_dtype = quant_state[2] if type(quant_state) is list else quant_state.dtype
+        dense = fast_dequantize(W, quant_state)                 # ub200_dequantize_nf4
+    merged = dense.float()                                       # [out, in], fp32
     if A is not None:
-        W.addmm_(A.t().to(torch.float32), B.t().to(torch.float32), alpha=s)
-        maximum_element = torch.max(W.min().abs(), W.max())
-        if not torch.isfinite(maximum_element).item():
-            raise ValueError("Unsloth: Merge failed.\n%s has some elements = infinity." % name)
-    return W.t().to(dtype), bias
+        merged = torch.addmm(merged, B.float(), A.float(), alpha=s)
+        if not bool(torch.isfinite(merged.abs().max())):
+            raise ValueError("unsloth_b200: merging the adapter of %r produced non-finite weights" % name)
+    return merged.to(out_dtype), bias
 
 
 def merged_state_dict(model):
