@@ -499,3 +499,109 @@ def test_fp16_model_runs_through_the_16bit_paths(cpu_model):
     l16.backward()
     assert torch.isfinite(l16) and abs(l16.item() - l32.item()) < 2e-2 * abs(l32.item())
     assert all(torch.isfinite(p.grad).all() for p in P.lora_parameters(m16))
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 advisor findings
+# ------------------------------------------------------------------------------------------------
+def test_lora_casts_never_go_stale_after_raw_parameter_updates(cpu_model):
+    """Optimisers that write parameters behind autograd's back (`p.data.add_()`, raw pointers,
+    8-bit / fused optimisers) bump neither `_version` nor PARAM_EPOCH: every forward rebuilds its
+    16-bit adapter casts, so the next step must see the new adapters."""
+    P = cpu_model
+    model = _build(P, "llama-3-8b")
+    torch.manual_seed(2)
+    ids = torch.randint(0, TINY["vocab_size"], (1, 12))
+    l0 = model(input_ids=ids, labels=ids).loss.item()
+    l0b = model(input_ids=ids, labels=ids).loss.item()
+    assert l0 == l0b
+    with torch.no_grad():
+        for p in P.lora_parameters(model):
+            p.data.add_(0.05 * torch.randn_like(p))          # no _version bump on `p`
+    l1 = model(input_ids=ids, labels=ids).loss.item()
+    assert abs(l1 - l0) > 1e-4, (l0, l1)
+    # the decode-time cast cache is refreshed by ANY torch.optim step (global post-step hook)
+    from unsloth_b200.kernels import utils as KU
+    e0 = KU.PARAM_EPOCH
+    opt = torch.optim.SGD(P.lora_parameters(model), lr=0.1)
+    model(input_ids=ids, labels=ids).loss.backward()
+    opt.step()
+    assert KU.PARAM_EPOCH > e0
+
+
+def test_fused_ce_trainable_lm_head_bias_and_loss_scaler(emu):
+    """unsloth_fused_ce_loss with a trainable lm_head (+ bias), a vocabulary that is not a multiple
+    of 8, and the fp16 GradScaler the reference call site passes as `scaling`
+    (models/llama.py:1505): same loss and gradients as autograd on the logits path; the scale is
+    folded into the in-pass gradient and divided out again."""
+    from unsloth_b200.kernels import unsloth_fused_ce_loss
+    torch.manual_seed(4)
+    Bz, S, H, V = 2, 70, 32, 203
+    hidden = torch.randn(Bz, S, H, requires_grad=True)
+    Wt = (torch.randn(V, H) * 0.2).requires_grad_()
+    bias = (torch.randn(V) * 0.1).requires_grad_()
+    labels = torch.randint(0, V, (Bz, S)); labels[0, 3] = -100
+
+    class Scaler:                                    # GradScaler surface used by the loss
+        def get_scale(self): return 1024.0
+        def is_enabled(self): return True
+    loss = unsloth_fused_ce_loss(trainer=None, hidden_states=hidden, lm_head_weight=Wt, lm_head_bias=bias,
+                                 labels=labels, mask=None, n_items=None, scaling=Scaler(), target_gb=None,
+                                 torch_compile=False, logit_softcapping=0, chunk_rows=128)
+    (loss * 3.0).backward()                          # an upstream factor must flow through unchanged
+    h2, W2, b2 = (t.detach().clone().requires_grad_() for t in (hidden, Wt, bias))
+    logits = h2 @ W2.t() + b2
+    shift = torch.full_like(labels, -100); shift[:, :-1] = labels[:, 1:]
+    ref = torch.nn.functional.cross_entropy(logits.view(-1, V), shift.view(-1), ignore_index=-100)
+    (ref * 3.0).backward()
+    close(loss, ref, atol=2e-5)
+    close(hidden.grad, h2.grad, atol=2e-5)
+    close(Wt.grad, W2.grad, atol=2e-5)
+    close(bias.grad, b2.grad, atol=2e-5)
+    # frozen lm_head (the QLoRA default): no weight-gradient work, no gradient
+    Wf = Wt.detach().clone()
+    h3 = hidden.detach().clone().requires_grad_()
+    unsloth_fused_ce_loss(hidden_states=h3, lm_head_weight=Wf, labels=labels, chunk_rows=128).backward()
+    h4 = hidden.detach().clone().requires_grad_()
+    torch.nn.functional.cross_entropy((h4 @ Wf.t()).view(-1, V), shift.view(-1), ignore_index=-100).backward()
+    close(h3.grad, h4.grad, atol=2e-5)
+    # no_grad: loss only
+    with torch.no_grad():
+        l = unsloth_fused_ce_loss(hidden_states=hidden, lm_head_weight=Wf, labels=labels, chunk_rows=128)
+    assert not l.requires_grad
+
+
+def test_rope_scaling_types():
+    import unsloth_b200.patch as P
+    base = P.RotaryCache(64, 10000.0, "cpu", torch.float32).inv_freq()
+    lin = P.RotaryCache(64, 10000.0, "cpu", torch.float32, dict(rope_type="linear", factor=4.0)).inv_freq()
+    assert torch.allclose(lin, base / 4.0)
+    with pytest.raises(NotImplementedError):
+        P.RotaryCache(64, 10000.0, "cpu", torch.float32, dict(rope_type="yarn", factor=4.0)).inv_freq()
+
+
+def test_no_grad_forward_does_not_keep_dequantised_weights(cpu_model):
+    from unsloth_b200.kernels import utils as KU
+    P = cpu_model
+    model = _build(P, "llama-3-8b")
+    KU.set_keep_dequant(True)
+    try:
+        ids = torch.randint(0, TINY["vocab_size"], (1, 8))
+        seen = []
+        orig = KU.fast_dequantize
+
+        def spy(W, qs=None, out=None, use_global_buffer=False, _slot=0):
+            seen.append(use_global_buffer)
+            return orig(W, qs, out, use_global_buffer, _slot)
+        KU.fast_dequantize = spy
+        try:
+            with torch.no_grad():
+                model(input_ids=ids, labels=ids)
+            assert seen and all(seen), "no_grad forward must reuse the global buffers"
+            seen.clear()
+            model(input_ids=ids, labels=ids).loss.backward()
+            assert not any(seen), "training forward keeps private expansions for the backward"
+        finally:
+            KU.fast_dequantize = orig
+    finally:
+        KU.set_keep_dequant(False)

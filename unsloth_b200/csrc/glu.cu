@@ -39,48 +39,83 @@ __device__ __forceinline__ void act_eval(float e, float& f, float& dfde) {
   }
 }
 
-template <typename T, int ACT>
+// Each thread keeps U independent 16-byte vectors of every operand in flight per iteration (the
+// loads of a batch are all issued before the first use): a grid-stride loop with ONE vector per
+// iteration left ~64 KB per SM outstanding, just under what 6.6 TB/s x ~1 us needs, and ran at
+// 0.88 of the measured copy bandwidth where the reference's Triton kernel (114,688 one-shot CTAs)
+// reached 1.0 (profiles/r2_ref_triton_ops.log).
+template <typename T, int ACT, int U>
 __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ e,
                                                       const T* __restrict__ g,
                                                       T* __restrict__ h, int64_t n_vec) {
   constexpr int V = DT<T>::VEC;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float ev[V], gv[V], o[V];
-    load_vec_cs<T>(e + i * V, ev);
-    load_vec_cs<T>(g + i * V, gv);
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n_vec; base += step) {
+    int4 er[U], gr[U];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float f, d;
-      act_eval<ACT, sizeof(T) == 2>(ev[k], f, d);
-      o[k] = DT<T>::rnd(f) * gv[k];
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n_vec) {
+        er[u] = __ldcs(reinterpret_cast<const int4*>(e + i * V));
+        gr[u] = __ldcs(reinterpret_cast<const int4*>(g + i * V));
+      }
     }
-    store_vec<T>(h + i * V, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i >= n_vec) break;
+      const T* ev = reinterpret_cast<const T*>(&er[u]);
+      const T* gv = reinterpret_cast<const T*>(&gr[u]);
+      float o[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float f, d;
+        act_eval<ACT, sizeof(T) == 2>(DT<T>::to_f(ev[k]), f, d);
+        o[k] = DT<T>::rnd(f) * DT<T>::to_f(gv[k]);
+      }
+      store_vec<T>(h + i * V, o);
+    }
   }
 }
 
-template <typename T, int ACT>
+template <typename T, int ACT, int U>
 __global__ void __launch_bounds__(256) glu_bwd_kernel(T* DW, T* e, T* g, int64_t n_vec) {
   constexpr int V = DT<T>::VEC;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float dw[V], ev[V], gv[V], oh[V], odf[V], ode[V];
-    load_vec_cs<T>(DW + i * V, dw);
-    load_vec_cs<T>(e + i * V, ev);
-    load_vec_cs<T>(g + i * V, gv);
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n_vec; base += step) {
+    int4 dr[U], er[U], gr[U];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float f, d;
-      act_eval<ACT, sizeof(T) == 2>(ev[k], f, d);
-      const float fr = DT<T>::rnd(f);
-      oh[k] = fr * gv[k];                    // h  = f * g
-      odf[k] = dw[k] * fr;                   // df = DW * f
-      const float dg = DT<T>::rnd(dw[k] * gv[k]);  // dg = DW * g (tensor dtype)
-      ode[k] = dg * d;                       // de = dg.float() * df/de
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i < n_vec) {
+        dr[u] = __ldcs(reinterpret_cast<const int4*>(DW + i * V));
+        er[u] = __ldcs(reinterpret_cast<const int4*>(e + i * V));
+        gr[u] = __ldcs(reinterpret_cast<const int4*>(g + i * V));
+      }
     }
-    store_vec<T>(DW + i * V, oh);
-    store_vec<T>(e + i * V, odf);
-    store_vec<T>(g + i * V, ode);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      if (i >= n_vec) break;
+      const T* dw = reinterpret_cast<const T*>(&dr[u]);
+      const T* ev = reinterpret_cast<const T*>(&er[u]);
+      const T* gv = reinterpret_cast<const T*>(&gr[u]);
+      float oh[V], odf[V], ode[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float f, d;
+        const float dwk = DT<T>::to_f(dw[k]), gk = DT<T>::to_f(gv[k]);
+        act_eval<ACT, sizeof(T) == 2>(DT<T>::to_f(ev[k]), f, d);
+        const float fr = DT<T>::rnd(f);
+        oh[k] = fr * gk;                        // h  = f * g
+        odf[k] = dwk * fr;                      // df = DW * f
+        const float dg = DT<T>::rnd(dwk * gk);  // dg = DW * g (tensor dtype)
+        ode[k] = dg * d;                        // de = dg.float() * df/de
+      }
+      store_vec<T>(DW + i * V, oh);
+      store_vec<T>(e + i * V, odf);
+      store_vec<T>(g + i * V, ode);
+    }
   }
 }
 
@@ -99,8 +134,8 @@ extern "C" int ub200_glu_fwd(int act, const void* e, const void* g, void* h, int
   const int V = dtype == UB200_F32 ? 4 : 8;
   if (n % V) return UB200_ERR_BAD_ARG;
   const int64_t nv = n / V;
-  const int grid = ew_grid(nv, 256);
-#define GO(T, A) glu_fwd_kernel<T, A><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv)
+  const int grid = ew_grid(nv, 256 * 4);
+#define GO(T, A) glu_fwd_kernel<T, A, 4><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv)
 #define GOA(T)                                                  \
   if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
   else if (act == ACT_GEGLU_APPROX) GO(T, ACT_GEGLU_APPROX);    \
@@ -122,8 +157,8 @@ extern "C" int ub200_glu_bwd(int act, void* DW, void* e, void* g, int64_t n, int
   const int V = dtype == UB200_F32 ? 4 : 8;
   if (n % V) return UB200_ERR_BAD_ARG;
   const int64_t nv = n / V;
-  const int grid = ew_grid(nv, 256);
-#define GO(T, A) glu_bwd_kernel<T, A><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv)
+  const int grid = ew_grid(nv, 256 * 2);
+#define GO(T, A) glu_bwd_kernel<T, A, 2><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv)
 #define GOA(T)                                                  \
   if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
   else if (act == ACT_GEGLU_APPROX) GO(T, ACT_GEGLU_APPROX);    \

@@ -34,12 +34,15 @@ template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return 
 // Each thread expands 16 packed bytes (32 weights, half a 64-block).  absmax is either a
 // ready fp32 array (absmax_f32 != null: bitsandbytes-compatible stage 2) or rebuilt on the fly
 // from the double-quantised statistics.
-template <typename T>
+// POW2: both block sizes are powers of two (always true for bitsandbytes' 64 / 256), so the block
+// indices are shifts; the generic instantiation keeps the 64-bit divisions (round-1 SASS: two
+// division sequences of ~100 instructions per 32 weights made the kernel issue-bound at 0.63 of HBM).
+template <typename T, bool POW2>
 __global__ void __launch_bounds__(256) dequant_nf4_kernel(
     const uint8_t* __restrict__ packed, const float* __restrict__ absmax_f32,
     const uint8_t* __restrict__ absmax_q, const float* __restrict__ code2,
     const float* __restrict__ absmax2, const float* __restrict__ offset, T* __restrict__ out,
-    int64_t n, int blocksize, int blocksize2) {
+    int64_t n, int blocksize, int blocksize2, int bs_shift, int bs2_shift) {
   __shared__ float lut[16];
   __shared__ int4 stage_all[8 * 32 * 4];   // 2 KB per warp, 8 warps
   if (threadIdx.x < 16) lut[threadIdx.x] = kNF4[threadIdx.x];
@@ -56,9 +59,10 @@ __global__ void __launch_bounds__(256) dequant_nf4_kernel(
     const int64_t e0 = ch * 32;
     const bool warp_fast = bs_ok && (ch0 + 32) * 32 <= n;          // all 32 lanes have a full chunk
     if (warp_fast) {
-      const int64_t blk = e0 / blocksize;
+      const int64_t blk = POW2 ? (e0 >> bs_shift) : e0 / blocksize;
+      const int64_t blk2 = POW2 ? (blk >> bs2_shift) : blk / blocksize2;
       const float am = absmax_f32 ? absmax_f32[blk]
-                                  : __fadd_rn(__fmul_rn(code2[absmax_q[blk]], absmax2[blk / blocksize2]), off);
+                                  : __fadd_rn(__fmul_rn(code2[absmax_q[blk]], absmax2[blk2]), off);
       const int4 raw = __ldcs(reinterpret_cast<const int4*>(packed + e0 / 2));
       const uint8_t* b = reinterpret_cast<const uint8_t*>(&raw);
       alignas(16) T o[32];
@@ -158,11 +162,17 @@ static void launch_dequant(const uint8_t* packed, const float* absmax_f32, const
   const int64_t chunks = (n + 31) / 32;
   static int occ = 0;       // resident CTAs per SM: launch exactly one persistent wave
   if (!occ) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dequant_nf4_kernel<T>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dequant_nf4_kernel<T, true>, 256, 0);
     if (occ < 1) occ = 1;
   }
-  dequant_nf4_kernel<T><<<grid_for(chunks, 256, occ), 256, 0, st>>>(
-      packed, absmax_f32, absmax_q, code2, absmax2, offset, (T*)out, n, blocksize, blocksize2);
+  auto lg2 = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  const int s1 = lg2(blocksize), s2 = lg2(blocksize2);
+  if (s1 >= 0 && s2 >= 0)
+    dequant_nf4_kernel<T, true><<<grid_for(chunks, 256, occ), 256, 0, st>>>(
+        packed, absmax_f32, absmax_q, code2, absmax2, offset, (T*)out, n, blocksize, blocksize2, s1, s2);
+  else
+    dequant_nf4_kernel<T, false><<<grid_for(chunks, 256, occ), 256, 0, st>>>(
+        packed, absmax_f32, absmax_q, code2, absmax2, offset, (T*)out, n, blocksize, blocksize2, 0, 0);
 }
 
 }  // namespace ub

@@ -18,7 +18,17 @@
 // `compute_dtype` reproduces the reference's rounding: the no-index
 // kernel evaluates in the TABLE dtype, the QK kernel in the promoted dtype; each product
 // and the sum round to that dtype.
+#include <cstdlib>
+
 #include "common.cuh"
+
+// default rounding modes of the packed 16-bit kernel (see rope_packed_kernel)
+#ifndef UB200_ROPE_MODE_BF16
+#define UB200_ROPE_MODE_BF16 0
+#endif
+#ifndef UB200_ROPE_MODE_F16
+#define UB200_ROPE_MODE_F16 0
+#endif
 
 namespace ub {
 
@@ -81,10 +91,24 @@ __global__ void __launch_bounds__(512) rope_kernel(
 // 68 % SM-pipe utilisation from scalar rounding emulation on a kernel that should wait on HBM.
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct Pk2;
-template <> struct Pk2<__nv_bfloat16> { using T2 = __nv_bfloat162; };
-template <> struct Pk2<__half> { using T2 = __half2; };
+template <> struct Pk2<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  __device__ static __forceinline__ float2 to_f2(T2 v) { return __bfloat1622float2(v); }
+  __device__ static __forceinline__ T2 from_f2(float2 v) { return __float22bfloat162_rn(v); }
+};
+template <> struct Pk2<__half> {
+  using T2 = __half2;
+  __device__ static __forceinline__ float2 to_f2(T2 v) { return __half22float2(v); }
+  __device__ static __forceinline__ T2 from_f2(float2 v) { return __float22half2_rn(v); }
+};
 
-template <typename T, int HP>
+// MODE selects where the 16-bit roundings fall (measured against the reference's Triton kernel run
+// natively on a B200, tests/test_gpu_vs_reference.py / benchmarks/probe_ref_numerics.py):
+//   0  every product and the sum rounded (what TRITON_INTERPRET=1 / numpy does: fp16 goldens)
+//   1  LLVM's fp-contract=fast form of `a*c - b*s`:  fma(a, c, -rn(b*s)) ; fma(b, c, rn(a*s))
+//   2  the other contraction:                        fma(-b, s, rn(a*c)) ; fma(a, s, rn(b*c))
+//   3  fp32 evaluation, one rounding at the store
+template <typename T, int HP, int MODE>
 __global__ void __launch_bounds__(512) rope_packed_kernel(
     T* Q, int64_t q_bs, int64_t q_hs, int64_t q_ss, T* K, int64_t k_bs, int64_t k_hs,
     int64_t k_ss, const T* __restrict__ cos, int64_t cos_rs, const T* __restrict__ sin,
@@ -132,8 +156,21 @@ __global__ void __launch_bounds__(512) rope_packed_kernel(
         V16 o1, o2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          o1.h[i] = __hsub2_rn(__hmul2_rn(x1[u].h[i], c.h[i]), __hmul2_rn(x2[u].h[i], sn.h[i]));
-          o2.h[i] = __hadd2_rn(__hmul2_rn(x2[u].h[i], c.h[i]), __hmul2_rn(x1[u].h[i], sn.h[i]));
+          if (MODE == 0) {
+            o1.h[i] = __hsub2_rn(__hmul2_rn(x1[u].h[i], c.h[i]), __hmul2_rn(x2[u].h[i], sn.h[i]));
+            o2.h[i] = __hadd2_rn(__hmul2_rn(x2[u].h[i], c.h[i]), __hmul2_rn(x1[u].h[i], sn.h[i]));
+          } else if (MODE == 1) {
+            o1.h[i] = __hfma2(x1[u].h[i], c.h[i], __hneg2(__hmul2_rn(x2[u].h[i], sn.h[i])));
+            o2.h[i] = __hfma2(x2[u].h[i], c.h[i], __hmul2_rn(x1[u].h[i], sn.h[i]));
+          } else if (MODE == 2) {
+            o1.h[i] = __hfma2(__hneg2(x2[u].h[i]), sn.h[i], __hmul2_rn(x1[u].h[i], c.h[i]));
+            o2.h[i] = __hfma2(x1[u].h[i], sn.h[i], __hmul2_rn(x2[u].h[i], c.h[i]));
+          } else {
+            const float2 a = Pk2<T>::to_f2(x1[u].h[i]), b = Pk2<T>::to_f2(x2[u].h[i]);
+            const float2 cc = Pk2<T>::to_f2(c.h[i]), ss = Pk2<T>::to_f2(sn.h[i]);
+            o1.h[i] = Pk2<T>::from_f2(make_float2(__fmaf_rn(a.x, cc.x, -__fmul_rn(b.x, ss.x)), __fmaf_rn(a.y, cc.y, -__fmul_rn(b.y, ss.y))));
+            o2.h[i] = Pk2<T>::from_f2(make_float2(__fmaf_rn(b.x, cc.x, __fmul_rn(a.x, ss.x)), __fmaf_rn(b.y, cc.y, __fmul_rn(a.y, ss.y))));
+          }
         }
         *reinterpret_cast<int4*>(p[u] + d0) = o1.q;
         *reinterpret_cast<int4*>(p[u] + half + d0) = o2.q;
@@ -182,16 +219,22 @@ extern "C" int ub200_rope_qk(void* Q, int64_t q_batch_stride, int64_t q_head_str
     if (pthreads > 512) pthreads = 512;
     const int64_t pg = (int64_t)UB_SM_COUNT * 12;
     const int pgrid = (int)(n_rows < pg ? n_rows : pg);
-    if (dtype == UB200_BF16)
-      rope_packed_kernel<__nv_bfloat16, HP><<<pgrid, pthreads, 0, stream>>>(
-          (__nv_bfloat16*)Q, q_batch_stride, q_head_stride, q_seq_stride, (__nv_bfloat16*)K, k_batch_stride,
-          k_head_stride, k_seq_stride, (const __nv_bfloat16*)cos, cos_row_stride, (const __nv_bfloat16*)sin,
-          sin_row_stride, indices, seqlen, n_heads_q, n_heads_k, head_dim, backward, n_rows);
-    else
-      rope_packed_kernel<__half, HP><<<pgrid, pthreads, 0, stream>>>(
-          (__half*)Q, q_batch_stride, q_head_stride, q_seq_stride, (__half*)K, k_batch_stride, k_head_stride,
-          k_seq_stride, (const __half*)cos, cos_row_stride, (const __half*)sin, sin_row_stride, indices,
-          seqlen, n_heads_q, n_heads_k, head_dim, backward, n_rows);
+    // rounding mode: see rope_packed_kernel.  UB200_ROPE_MODE overrides (numerics probes only).
+    static const int env_mode = [] { const char* e = getenv("UB200_ROPE_MODE"); return e ? atoi(e) : -1; }();
+    const int mode = env_mode >= 0 ? env_mode : (dtype == UB200_BF16 ? UB200_ROPE_MODE_BF16 : UB200_ROPE_MODE_F16);
+#define GOP(T, M)                                                                                   \
+  rope_packed_kernel<T, HP, M><<<pgrid, pthreads, 0, stream>>>(                                     \
+      (T*)Q, q_batch_stride, q_head_stride, q_seq_stride, (T*)K, k_batch_stride, k_head_stride,     \
+      k_seq_stride, (const T*)cos, cos_row_stride, (const T*)sin, sin_row_stride, indices, seqlen, \
+      n_heads_q, n_heads_k, head_dim, backward, n_rows)
+#define GOM(T)                                                                                      \
+  do {                                                                                              \
+    if (mode == 1) GOP(T, 1); else if (mode == 2) GOP(T, 2); else if (mode == 3) GOP(T, 3); else GOP(T, 0); \
+  } while (0)
+    if (dtype == UB200_BF16) GOM(__nv_bfloat16);
+    else GOM(__half);
+#undef GOM
+#undef GOP
     UB_RETURN_LAST();
   }
 #define GO(T)                                                                                  \

@@ -22,8 +22,8 @@ import os
 import torch
 
 from .. import _lib as L
-from .utils import (RANK_BLOCK, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
-                    keep_dequant, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
+from .utils import (GradModeAware, RANK_BLOCK, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
+                    keep_dequant, keep_for_backward, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
                     matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
 from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
@@ -95,13 +95,13 @@ class _Group:
         self._A_cat = None
 
     # [Rp, in] : rows offs[i].. hold A_i in the compute dtype, zero elsewhere
-    def A_cat(self):
+    def A_cat(self, refresh=False):
         if self._A_cat is None:
             blocks = [(o, A) for o, (_, _, A, _, _) in zip(self.offs, self.projs) if A is not None]
             if len(blocks) == 1 and blocks[0][0] == 0:
                 A = blocks[0][1]
                 A = A if A.stride(-1) == 1 else A.contiguous()
-                self._A_cat = cached_cast_pad(A, (self.Rp, self.in_f), self.dtype)
+                self._A_cat = cached_cast_pad(A, (self.Rp, self.in_f), self.dtype, refresh=refresh)
                 return self._A_cat
             # several adapters share the rank block: memoise on the first adapter's Parameter,
             # keyed by the versions of all of them
@@ -109,7 +109,7 @@ class _Group:
             ver = tuple((A._version, A.data_ptr()) for _, A in blocks) + (_epoch(),)
             cache = first.__dict__.setdefault("_ub200_acat_cache", {}) if isinstance(first, torch.nn.Parameter) else None
             key = (self.Rp, self.in_f, self.dtype, tuple(o for o, _ in blocks))
-            if cache is not None:
+            if cache is not None and not refresh:
                 hit = cache.get(key)
                 if hit is not None and hit[0] == ver:
                     self._A_cat = hit[1]
@@ -132,7 +132,7 @@ class _Group:
             self.dense = []
         XA = None
         if self.has_lora:
-            XA = gemm(T, self.Rp, [(X2, self.A_cat(), self.in_f)],
+            XA = gemm(T, self.Rp, [(X2, self.A_cat(refresh=True), self.in_f)],
                       torch.empty((T, self.Rp), dtype=dt, device=dev))
         outs = []
         for off, (W, Wq, A, B, s) in zip(self.offs, self.projs):
@@ -145,9 +145,10 @@ class _Group:
             if A is not None:
                 Bc = B if B.stride(-1) == 1 else B.contiguous()
                 if b_mn:
-                    B_pad = cached_cast_pad(Bc, (self.Rp, N), dt, row_off=off, scale=s, transpose=True)
+                    B_pad = cached_cast_pad(Bc, (self.Rp, N), dt, row_off=off, scale=s, transpose=True,
+                                            refresh=True)
                 else:
-                    B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s)
+                    B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s, refresh=True)
                 segs.append((XA, B_pad, self.Rp))
             Y = torch.empty((T, N), dtype=dt, device=dev)
             gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
@@ -229,7 +230,7 @@ class _Group:
         return dX, grads
 
 
-class LoRA_MLP(torch.autograd.Function):
+class LoRA_MLP(GradModeAware, torch.autograd.Function):
     """fast_lora.py:28-229.  i = down(act(gate(X)) * up(X)), each projection NF4 + LoRA."""
 
     @staticmethod
@@ -241,7 +242,7 @@ class LoRA_MLP(torch.autograd.Function):
         shape = X.shape
         X2 = _as2d(X)
         grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
-        keep = keep_dequant() and any(ctx.needs_input_grad)
+        keep = keep_for_backward(ctx.needs_input_grad)
         (e, g), XA1 = grp.forward(keep)
         b_s = shape[:-1]
         h = _forward_function(e.view(*b_s, -1) if X.dim() == 3 else e.view(1, *e.shape),
@@ -346,7 +347,7 @@ def apply_lora_mlp_geglu_approx(self, X):
                           geglu_approx_forward_kernel, geglu_approx_backward_kernel)
 
 
-class LoRA_QKV(torch.autograd.Function):
+class LoRA_QKV(GradModeAware, torch.autograd.Function):
     """fast_lora.py:335-540."""
 
     @staticmethod
@@ -358,7 +359,7 @@ class LoRA_QKV(torch.autograd.Function):
         X2 = _as2d(X)
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
                           (VW, VW_quant, VA, VB, VS)])
-        (Q, K, V), XA = grp.forward(keep_dequant() and any(ctx.needs_input_grad))
+        (Q, K, V), XA = grp.forward(keep_for_backward(ctx.needs_input_grad))
         ctx.dense = grp.dense
         if len(shape) == 3:
             Q, K, V = (t.view(shape[0], shape[1], -1) for t in (Q, K, V))
@@ -394,7 +395,7 @@ def apply_lora_qkv(self, X, inplace=True):
                           VA, VB, VS, inplace)
 
 
-class LoRA_W(torch.autograd.Function):
+class LoRA_W(GradModeAware, torch.autograd.Function):
     """fast_lora.py:574-650 (o_proj)."""
 
     @staticmethod
@@ -404,7 +405,7 @@ class LoRA_W(torch.autograd.Function):
         shape = X.shape
         X2 = _as2d(X)
         grp = _Group(X2, [(W, W_quant, A, B, S)])
-        (XW,), XA = grp.forward(keep_dequant() and any(ctx.needs_input_grad))
+        (XW,), XA = grp.forward(keep_for_backward(ctx.needs_input_grad))
         ctx.dense = grp.dense
         ctx.custom_saved_tensors = (W, W_quant, S)
         ctx.lora = (A, B)

@@ -117,9 +117,10 @@ def _fast_lora_cast(A, B, dtype):
     the activation dtype for decoding (refreshed when the parameter is updated in place)."""
     for p_ in (A, B):
         c = getattr(p_, "_fast_lora", None)
-        if c is None or c.dtype != dtype or getattr(p_, "_fast_lora_version", None) != p_._version:
+        ver = (p_._version, PARAM_EPOCH, p_.data_ptr())
+        if c is None or c.dtype != dtype or getattr(p_, "_fast_lora_version", None) != ver:
             p_._fast_lora = p_.detach().to(dtype).contiguous()
-            p_._fast_lora_version = p_._version
+            p_._fast_lora_version = ver
     return A._fast_lora, B._fast_lora
 
 
@@ -224,8 +225,16 @@ def cast_pad(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
     return dst
 
 
-# Parameters updated behind autograd's back (ub200_adamw_flat writes through raw pointers and does
-# not bump tensor._version) bump this epoch so cached casts are rebuilt.
+# Cached 16-bit casts of the LoRA parameters.  Validity rules:
+#   * every FORWARD of a projection rebuilds its casts (`refresh=True`) -- a cast is only ever
+#     REUSED by the backward of the same forward (and by a later segment of the same step), so an
+#     optimiser that writes parameters behind autograd's back (`p.data.add_()`, raw pointers, 8-bit
+#     / fused optimisers: none of them bump `tensor._version`) can never leave a stale adapter in a
+#     training step;
+#   * lookups outside a forward (backward, decode-time `_fast_lora`) are keyed by
+#     (`_version`, PARAM_EPOCH, `data_ptr`); PARAM_EPOCH is bumped by ub200_adamw_flat's wrapper
+#     and by a global `torch.optim.Optimizer` post-step hook, and `bump_param_epoch()` is public
+#     for anything else that edits parameters in place between decode calls.
 PARAM_EPOCH = 0
 
 
@@ -234,16 +243,29 @@ def bump_param_epoch():
     PARAM_EPOCH += 1
 
 
-def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpose=False):
-    """`cast_pad` into a fresh [shape] tensor, memoised ON the source nn.Parameter (LoRA A / B
-    change once per optimiser step, not once per call).  Non-Parameter sources are never cached."""
+def _optimizer_post_step(optimizer, args, kwargs):
+    bump_param_epoch()
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(_optimizer_post_step)
+except Exception:  # pragma: no cover - very old torch
+    pass
+
+
+def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpose=False,
+                    refresh=False):
+    """`cast_pad` into a fresh [shape] tensor, memoised ON the source nn.Parameter so that the
+    backward reuses the cast its forward made.  `refresh=True` (every forward) rebuilds it
+    unconditionally; see PARAM_EPOCH above.  Non-Parameter sources are never cached."""
     if not isinstance(src, torch.nn.Parameter):
         return cast_pad(src, torch.empty(shape, dtype=dtype, device=src.device), row_off, col_off,
                         scale, transpose)
     cache = src.__dict__.setdefault("_ub200_cast_cache", {})
     key = (tuple(shape), dtype, row_off, col_off, float(scale), bool(transpose))
     ver = (src._version, PARAM_EPOCH, src.data_ptr())
-    hit = cache.get(key)
+    hit = None if refresh else cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
     dst = cast_pad(src, torch.empty(shape, dtype=dtype, device=src.device), row_off, col_off, scale,
@@ -268,8 +290,47 @@ def keep_dequant() -> bool:
             _KEEP_DEQUANT = True
         else:
             _KEEP_DEQUANT = (torch.cuda.is_available()
-                             and torch.cuda.get_device_properties(0).total_memory >= 128 * 2 ** 30)
+                             and torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+                             >= 128 * 2 ** 30)
     return _KEEP_DEQUANT
+
+
+# set by patch.install(gradient_checkpointing=True): with per-layer recompute the forward's 16-bit
+# expansions must not stay alive across layers (that is the memory the recompute is meant to save)
+KEEP_DEQUANT_BLOCKED = False
+
+
+import threading as _threading
+
+_OUTER = _threading.local()
+
+
+class GradModeAware:
+    """Mixin for autograd Functions: records the caller's grad mode around `apply`.  Inside
+    `Function.forward` grad mode is always off and `ctx.needs_input_grad` stays True under
+    `torch.no_grad()`, so this is the only way a forward can tell that no backward will follow."""
+
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        prev = getattr(_OUTER, "grad", None)
+        _OUTER.grad = torch.is_grad_enabled()
+        try:
+            return super().apply(*args, **kwargs)
+        finally:
+            _OUTER.grad = prev
+
+
+def outer_grad_enabled() -> bool:
+    g = getattr(_OUTER, "grad", None)
+    return True if g is None else g
+
+
+def keep_for_backward(needs_input_grad) -> bool:
+    """Should this forward keep its dequantised weights for the backward?  Only when a backward
+    will actually run (caller in grad mode, some input needs a gradient) and per-layer recompute
+    is not in charge of the memory."""
+    return (keep_dequant() and not KEEP_DEQUANT_BLOCKED and outer_grad_enabled()
+            and any(needs_input_grad))
 
 
 def set_keep_dequant(value):

@@ -71,7 +71,15 @@ class RotaryCache:
     def inv_freq(self):
         inv = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.int64).float() / self.dim))
         rs = self.rope_scaling
-        if rs and rs.get("rope_type", rs.get("type")) == "llama3":
+        kind = (rs.get("rope_type", rs.get("type")) if rs else None) or "default"
+        if kind == "linear":
+            # LlamaLinearScalingRotaryEmbedding (models/llama.py:1917-1960): positions / factor
+            inv = inv / float(rs["factor"])
+        elif kind not in ("default", "llama3"):
+            raise NotImplementedError(
+                "unsloth_b200: rope scaling %r is not implemented (default, linear and llama3 are); "
+                "refusing to train with unscaled frequencies" % kind)
+        if kind == "llama3":
             factor, lo, hi = rs["factor"], rs["low_freq_factor"], rs["high_freq_factor"]
             old = rs["original_max_position_embeddings"]
             low_wl, high_wl = old / lo, old / hi
@@ -186,17 +194,25 @@ def Model_fast_forward(self, input_ids, position_ids=None, packed_seq_lengths=No
         h = h * torch.tensor(math.sqrt(self.config.hidden_size), dtype=h.dtype, device=h.device)
     seq_len = input_ids.shape[1]
     need = seq_len
-    cos, sin = self._ub_rotary.get(need)
     # packed / padding-free rows (llama.py:706, :721-723): per-document attention through
     # cu_seqlens and RoPE through the reset-style position ids (derived when the collator
     # did not send them)
     seq_info = get_packed_info_from_kwargs({"packed_seq_lengths": packed_seq_lengths}, h.device,
                                            input_ids.numel())
-    if seq_info is not None and position_ids is None:
+    derived = seq_info is not None and position_ids is None
+    if derived:
         position_ids = packed_position_ids(packed_seq_lengths, input_ids.numel(), h.device)
     idx = None
     if position_ids is not None:
         idx = position_ids.reshape(-1).to(torch.int32)
+        if idx.numel() != input_ids.numel():
+            raise ValueError("unsloth_b200: position_ids must hold one entry per token (%d != %d)"
+                             % (idx.numel(), input_ids.numel()))
+        # caller-supplied positions may exceed the row length: size the table for the model's
+        # position range (no device sync to read the actual maximum); packed positions are < seq_len
+        if not derived:
+            need = max(need, int(getattr(self.config, "max_position_embeddings", 0) or 0))
+    cos, sin = self._ub_rotary.get(need)
     # optional recompute of every decoder layer in the backward (the plain-recompute part of the
     # reference's use_gradient_checkpointing, models/llama.py:1169-1192; no activation offload):
     # not needed for the BASELINE configs on a 180 GB B200, available for longer sequences
@@ -257,8 +273,10 @@ def CausalLM_fast_forward(self, input_ids=None, labels=None, position_ids=None,
         return SimpleNamespace(loss=None, logits=None, hidden_states=hidden)
     labels = mask_packed_boundary_labels(labels, packed_seq_lengths)
     loss = K.unsloth_fused_ce_loss(
-        trainer=None, hidden_states=hidden, lm_head_weight=self.lm_head.weight, lm_head_bias=None,
-        labels=labels, mask=None, n_items=num_items_in_batch, scaling=None, target_gb=None,
+        trainer=None, hidden_states=hidden, lm_head_weight=self.lm_head.weight,
+        lm_head_bias=getattr(self.lm_head, "bias", None),
+        labels=labels, mask=None, n_items=num_items_in_batch,
+        scaling=getattr(self, "accelerator_scaler", None), target_gb=None,
         torch_compile=False, logit_softcapping=self._ub_final_softcap)
     return SimpleNamespace(loss=loss, logits=None, hidden_states=None)
 
@@ -295,6 +313,10 @@ def install(model, gradient_checkpointing=False):
                                    torch.float32 if gemma else dtype, rope_scaling)
     inner._ub_gemma = gemma
     inner._ub_gradient_checkpointing = bool(gradient_checkpointing)
+    if gradient_checkpointing:
+        # per-layer recompute owns the memory: do not keep 16-bit expansions alive across layers
+        from .kernels import utils as _KU
+        _KU.KEEP_DEQUANT_BLOCKED = True
     model._ub_final_softcap = float(getattr(cfg, "final_logit_softcapping", 0) or 0)
     mlp_fn = K.apply_lora_mlp_geglu_approx if gemma else K.apply_lora_mlp_swiglu   # llama.py:3618-3639
     for i, layer in enumerate(inner.layers):
