@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu-reference"],
+                    help="ours | reference (the reference's CPU path, this tier's reference arm) | gpu-reference "
+                         "(the reference's own GPU kernels on the B200: BASELINE.md B1/B3)")
     ap.add_argument("--model", default=MODEL)
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer layers (INVALID as a bench)")
     ap.add_argument("--seq", type=int, default=SEQ)
@@ -61,7 +63,10 @@ def parse():
                     help="re-dequantise the NF4 weights in the backward (the reference's schedule) instead of "
                          "keeping the forward's 16-bit expansion resident until the layer's backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-tokens", type=int, default=512)
+    ap.add_argument("--cpu-sample-tokens", type=int, default=None,
+                    help="tokens of the CPU arm's bounded sample (default: one row of --seq tokens)")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip timing the reference's GPU path (Triton kernels + cuBLAS LoRA schedule) beside ours")
     a = ap.parse_args()
     if a.preset == "cfg3":
         a.model, a.seq, a.bs, a.rank = "mistral-7b-v0.3", 4096, 2, 32
@@ -127,31 +132,37 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # the reference's CPU path: torch eager fp32, stock HF Llama + plain LoRA
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_tokens_per_sec(model_name, seq_tokens, r=RANK_R, threads=None, reps=2, max_seconds=150.0):
+def host_threads():
+    """A FIXED thread count for the CPU arm: the cores this process may actually use (affinity
+    mask and cgroup CPU quota), capped at 64 -- torch's CPU GEMMs stop scaling beyond that and an
+    over-subscribed quota collapses them (round 1: 1.3 tokens/s with 128 threads on a box whose
+    quota was lower).  No per-run probing: the same box always gets the same number."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
+def cpu_reference_tokens_per_sec(model_name, seq_tokens, r=RANK_R, threads=None, reps=3, depths=(1, 2)):
     """Times forward+backward of the stock HuggingFace implementation on the host cores for a
-    BOUNDED sample: `seq_tokens` tokens (batch 1) through models with 1 and 2 decoder layers of
-    the named architecture; per-layer and head costs are separated by differencing and
-    extrapolated to the full depth.  Returns (tokens/s of the full model, description)."""
+    BOUNDED sample: `seq_tokens` tokens (one row at the workload's full sequence length) through
+    models with `depths` decoder layers of the named architecture, `reps` timed repetitions each
+    after one warm-up, MEDIAN taken; per-layer and embed/lm_head/CE costs separated by differencing
+    and extrapolated to the full depth.  Imports nothing from unsloth_b200 (the arm must not load
+    the product).  Returns (tokens/s of the full model, description, threads, spread)."""
     import torch
     from torch import nn
-    from unsloth_b200.patch import hf_config, CONFIGS
+    from unsloth_b200.model_configs import CONFIGS, hf_config
 
-    if threads is None:
-        # use the thread count at which this host's torch CPU GEMM is actually fastest (on many-core
-        # hosts "all cores" can be slower than a subset): probe a projection-sized matmul
-        cores = os.cpu_count() or 1
-        a, b = torch.randn(seq_tokens, 4096), torch.randn(4096, 4096)
-        best_t, best = cores, None
-        for cand in sorted({cores, max(1, cores // 2), min(cores, 64), min(cores, 32)}, reverse=True):
-            torch.set_num_threads(cand)
-            a @ b
-            t0 = time.perf_counter()
-            for _ in range(3):
-                a @ b
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, best_t = dt, cand
-        threads = best_t
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     full_layers = CONFIGS[model_name]["num_hidden_layers"]
 
@@ -167,7 +178,7 @@ def cpu_reference_tokens_per_sec(model_name, seq_tokens, r=RANK_R, threads=None,
         def forward(self, x):
             return self.lin(x) + self.s * (x @ self.A.t()) @ self.B.t()
 
-    def step_time(n_layers):
+    def step_times(n_layers):
         from transformers import AutoModelForCausalLM
         cfg = hf_config(model_name, n_layers)
         cfg._attn_implementation = "sdpa"
@@ -181,49 +192,45 @@ def cpu_reference_tokens_per_sec(model_name, seq_tokens, r=RANK_R, threads=None,
                     if hasattr(parent, nme):
                         setattr(parent, nme, PlainLoRA(getattr(parent, nme), r, r))
         ids = torch.randint(0, cfg.vocab_size, (1, seq_tokens))
-        best = None
-        t_begin = time.perf_counter()
+        ts = []
         for i in range(reps + 1):
             t0 = time.perf_counter()
             out = m(input_ids=ids, labels=ids)
             out.loss.backward()
-            dt = time.perf_counter() - t0
             if i > 0:
-                best = dt if best is None else min(best, dt)
-            if time.perf_counter() - t_begin > max_seconds / 2 and best is not None:
-                break
+                ts.append(time.perf_counter() - t0)
         del m
-        return best
+        return ts
 
-    t1 = step_time(1)
-    t2 = step_time(2)
-    per_layer = max(t2 - t1, 1e-9)
-    head = max(t1 - per_layer, 0.0)
+    times = {d: step_times(d) for d in depths}
+    med = {d: statistics.median(t) for d, t in times.items()}
+    d0, d1 = depths[0], depths[-1]
+    per_layer = max((med[d1] - med[d0]) / max(d1 - d0, 1), 1e-9)
+    head = max(med[d0] - per_layer * d0, 0.0)
     full = head + per_layer * full_layers
-    desc = ("stock HF %s (transformers, torch eager, fp32, device=cpu) + plain LoRA r=%d, fwd+bwd of "
-            "1x%d tokens; 1- and 2-layer models timed (%.2fs, %.2fs), per-layer cost extrapolated to %d "
-            "layers + embed/lm_head/CE" % (model_name, r, seq_tokens, t1, t2, full_layers))
-    return seq_tokens / full, desc, threads
+    spread = {str(d): [round(min(t), 3), round(max(t), 3)] for d, t in times.items()}
+    desc = ("stock HF %s (transformers, torch eager, fp32, device=cpu) + plain LoRA r=%d, fwd+bwd of 1x%d "
+            "tokens; %s-layer models, %d reps each after 1 warm-up, medians %s s (min/max %s); per-layer cost "
+            "extrapolated to %d layers + embed/lm_head/CE; %d threads (fixed rule: usable cores capped at 64)"
+            % (model_name, r, seq_tokens, "/".join(map(str, depths)), reps,
+               "/".join("%.2f" % med[d] for d in depths), json.dumps(spread), full_layers, threads))
+    return seq_tokens / full, desc, threads, spread
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    vals = []
-    desc, threads = "", os.cpu_count()
-    n = max(1, min(args.steps, 2))        # each "step" is the bounded sample; keep the run to minutes
-    for _ in range(n):
-        v, desc, threads = cpu_reference_tokens_per_sec(args.model, args.cpu_sample_tokens, reps=1)
-        vals.append(v)
-    v = statistics.median(vals)
+    v, desc, threads, spread = cpu_reference_tokens_per_sec(args.model, args.cpu_sample_tokens or args.seq,
+                                                             r=args.rank, reps=max(3, min(args.steps, 5)))
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(args.bs * args.seq / v * 1e3, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "%s QLoRA r=%d seq%d bs%d/GPU (reference CPU path: torch eager fp32)" %
-                                   (args.model, RANK_R, args.seq, args.bs)},
-            "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc},
+                                   (args.model, args.rank, args.seq, args.bs)},
+            "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": desc, "spread_s": spread},
             "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -348,32 +355,51 @@ def run_ours(args):
     if os.path.exists(pp):
         d = json.load(open(pp))
         peaks = {"bf16_tflops_sustained": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "src": "measured (MEASURED_PEAKS.json, sustained)"}
-    roof = None
+    roof, roof_all = None, None
     if gemm_events:
-        big = [(fl, s_.elapsed_time(e_)) for (fl, s_, e_) in gemm_events if fl >= 1e10]
-        if big:
-            tot_fl = sum(f for f, _ in big); tot_ms = sum(t for _, t in big)
-            ach = tot_fl / tot_ms / 1e9
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-            if os.path.exists(tp):
-                traffic = json.load(open(tp)).get("gemm_kernel_dram_bytes_per_launch")
-            roof = {"bound": "tensor", "kernel": "ub::gemm::gemm2_kernel<256> (tcgen05 cta_group::2 multi-segment GEMM; all launches >= 10 GFLOP)",
-                    "achieved": round(ach, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": round(ach / peaks["bf16_tflops_sustained"], 3), "traffic": traffic,
-                    "peak_source": peaks["src"], "launches_timed": len(big),
-                    "avg_launch_ms": round(tot_ms / len(big), 4),
-                    "share_of_step": round(tot_ms / ms_prof, 3),
-                    "timing": "CUDA-event pair around every launch during an eager pass of the same %d steps "
-                              "(%.2f ms/step; events cannot be read inside a replayed graph)" % (args.steps, ms_prof / args.steps)}
+        # one entry per kernel: algorithmic flops (true LoRA rank, not the zero-padded rank block)
+        # over the summed CUDA-event durations of that kernel's launches
+        names = {"grouped": "ub::gemm::grouped::gemm_grouped_kernel (persistent tcgen05 cta_group::2; dense GEMMs + "
+                            "rank-block producers + split-K dA/dB of a LoRA phase in one launch)",
+                 "gemm2": "ub::gemm::gemm2_kernel (tcgen05 cta_group::2 multi-segment GEMM: lm_head / fused-CE chunks)",
+                 "gemm1": "ub::gemm::gemm_kernel (single-CTA tcgen05 GEMM: tails / small problems)"}
+        agg = {}
+        for (fl, s_, e_, info) in gemm_events:
+            a_ = agg.setdefault(info["kernel"], {"flops": 0.0, "ms": 0.0, "n": 0, "rank_flops": 0.0})
+            a_["flops"] += fl; a_["ms"] += s_.elapsed_time(e_); a_["n"] += 1
+            a_["rank_flops"] += info.get("rank_flops", 0.0)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("gemm_kernel_dram_bytes_per_launch")
+        roof_all = []
+        for k_, a_ in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            ach = a_["flops"] / a_["ms"] / 1e9
+            roof_all.append({"bound": "tensor", "kernel": names.get(k_, k_), "achieved": round(ach, 1),
+                             "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": round(ach / peaks["bf16_tflops_sustained"], 3),
+                             "launches_timed": a_["n"], "avg_launch_ms": round(a_["ms"] / a_["n"], 4),
+                             "share_of_step": round(a_["ms"] / ms_prof, 3),
+                             "rank_block_flops_share": round(a_["rank_flops"] / max(a_["flops"], 1.0), 4)})
+        roof = dict(roof_all[0])
+        roof.update({"traffic": traffic, "peak_source": peaks["src"],
+                     "flops": "algorithmic: 2*M*N*K per product with the TRUE LoRA rank for rank-block segments",
+                     "timing": "CUDA-event pair around every launch during an eager pass of the same %d steps "
+                               "(%.2f ms/step; events cannot be read inside a replayed graph)" % (args.steps, ms_prof / args.steps)})
 
+    # ---- the reference's own GPU path on this box, N = 1 only ----------------
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference and not args.gradient_checkpointing:
+        gpu_ref = gpu_reference_leg(model, dev_ids, dev_lab, args)
     if rank != 0:
         return 0
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, desc, threads = cpu_reference_tokens_per_sec(args.model, args.cpu_sample_tokens, reps=1)
-            cpu = {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc}
+            v, desc, threads, spread = cpu_reference_tokens_per_sec(args.model, args.cpu_sample_tokens or args.seq,
+                                                                     r=args.rank, reps=3)
+            cpu = {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc,
+                   "spread_s": spread}
         except Exception as ex:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % ex}
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -395,10 +421,63 @@ def run_ours(args):
                     "h2d_bytes_per_step": 2 * args.bs * args.seq * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "peak_vram_gib": round(peak_vram, 2),
             "loss": {"resident_last": round(loss_res, 4), "e2e_last": round(loss_e2e, 4)},
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+            "roofline": roof, "roofline_by_kernel": roof_all, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "clocks": clocks}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def gpu_reference_leg(model, dev_ids, dev_lab, args, attentions=("flash", "sdpa")):
+    """Times the REFERENCE's GPU path on the same model object and batches: its Triton kernels
+    (compiled natively for the B200), its LoRA autograd functions with their cuBLAS schedule and its
+    `fast_dequantize` host path (benchmarks/ref_composite.py; the unmodified install under
+    baseline/_ref).  `flash` = flash-attn 2, the backend the reference's dispatcher prefers;
+    `sdpa` = cuDNN fused attention, its best case.  Returns None-with-reason if unavailable."""
+    try:
+        import torch
+        from oracle import ref_shim
+        if not ref_shim.reference_available():
+            return {"unavailable": "reference not installed under baseline/_ref (DESIGN.md section 5)"}
+        from benchmarks.ref_composite import time_reference_step
+        res = {}
+        for attn in attentions:
+            r = time_reference_step(model, dev_ids, dev_lab, steps=max(3, min(args.steps, 8)),
+                                    warmup=max(2, min(args.warmup, 3)), attention=attn)
+            res[attn] = {"value": round(r["tokens_per_s"], 1), "unit": UNIT, "ms_per_step": round(r["ms_per_step"], 2),
+                         "peak_vram_gib": round(r["peak_vram_gib"], 2), "loss_last": round(r["loss_last"], 4),
+                         "steps": r["steps"], "warmup": r["warmup"]}
+            torch.cuda.empty_cache()
+        best = max(res.values(), key=lambda d: d["value"])
+        return {"value": best["value"], "unit": UNIT, "by_attention_backend": res,
+                "what": "reference Unsloth GPU path: its Triton kernels + LoRA_MLP/QKV/W autograd functions (cuBLAS "
+                        "torch.matmul/addmm_ schedule) + its fast_dequantize host path on libunsloth_b200.so's "
+                        "bitsandbytes-signature symbols (bitsandbytes absent), materialised-logits loss route "
+                        "(llama.py:1525-1562), eager launches, torch fused AdamW; value = best backend"}
+    except Exception as ex:  # pragma: no cover - report, never fail the bench line
+        return {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+
+
+def run_gpu_reference(args):
+    """`--impl gpu-reference`: only the reference's GPU path (same JSON shape as our line)."""
+    import torch
+    from unsloth_b200.patch import build_qlora_model
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    dev = torch.device("cuda", 0)
+    model = build_qlora_model(args.model, r=args.rank, lora_alpha=args.rank, device=dev, seed=3407,
+                              num_hidden_layers=args.layers)
+    g = torch.Generator().manual_seed(1234)
+    n = args.warmup + args.steps
+    ids = torch.randint(0, model.config.vocab_size, (n, args.bs, args.seq), generator=g)
+    lab = ids.clone()
+    lab[torch.rand(lab.shape, generator=g) < 0.1] = -100
+    r = gpu_reference_leg(model, ids.to(dev), lab.to(dev), args)
+    line = {"impl": "gpu-reference", "metric": METRIC, "value": r.get("value"), "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "%s QLoRA NF4 r=%d bf16 seq%d bs%d/GPU" % (args.model, args.rank, args.seq, args.bs)},
+            "gpu_reference": r}
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -406,6 +485,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "gpu-reference":
+        return run_gpu_reference(args)
     return run_ours(args)
 
 

@@ -207,6 +207,45 @@ int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_m
                cudaStream_t stream);
 int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* bytes);
 
+/* ---- grouped tcgen05 GEMM: one persistent launch for a whole phase of a LoRA projection group --
+ * All GEMMs the reference issues for one phase of LoRA_MLP / LoRA_QKV / LoRA_W (forward: X@A, the
+ * dense products with the rank update; backward: dY@B, the dX sum, and the dA / dB reductions over
+ * tokens -- unsloth/kernels/fast_lora.py:116-229, 432-540, 617-650) as a LIST of problems
+ *      C_p[M_p,N_p] = alpha_p * sum_s A_ps . B_ps^T   (+ C_p if accumulate)
+ * walked by one persistent grid (csrc/gemm_grouped.cu).  Operand conventions as ub200_gemm.
+ *   block_n      64 / 128 / 256 output columns per tile (MN-major B needs >= 128; N may be smaller
+ *                than block_n: TMA zero-fills the missing columns)
+ *   split_k > 1  fp32 `workspace` [split_k, M, N]; the last split to arrive reduces in fixed order
+ *   signals      consumers in the same launch may wait on this problem's output
+ *   wait_problem index (< own index) of a problem of this launch that PRODUCES an operand of this
+ *                one, or -1; wait_segment: first segment that reads it.  wait_all == 0: the producer's
+ *                rows [256 m, 256 m + 256) are needed by this problem's row block m (the operand is
+ *                a K-major A with the same M); wait_all != 0: the whole producer output is needed
+ *                (it is a reduction operand, e.g. dA = X^T @ G).
+ * `scratch`: ub200_gemm_grouped_scratch_ints() int32s, ZERO before the first use; the kernel
+ * leaves it zero again (CUDA-graph replays need no memset).  One scratch buffer per stream.     */
+#define UB200_GROUPED_MAX_PROBLEMS 8
+#define UB200_GROUPED_MAX_SEGMENTS 4
+typedef struct {
+  int M, N;
+  const ub200_gemm_segment* segs;
+  int n_segs;
+  int a_mn_major, b_mn_major;
+  void* C;
+  int64_t ldc;
+  int c_dtype;
+  float alpha;
+  int accumulate;
+  int split_k;
+  void* workspace;
+  int block_n;
+  int signals;
+  int wait_problem, wait_segment, wait_all;
+} ub200_gemm_problem;
+int ub200_gemm_grouped(const ub200_gemm_problem* probs, int n_probs, int ab_dtype, int* scratch,
+                       cudaStream_t stream);
+int ub200_gemm_grouped_scratch_ints(const ub200_gemm_problem* probs, int n_probs, int* ints);
+
 /* ---- small helpers of the LoRA path ---------------------------------------------------------
  * Writes the whole [dst_rows, dst_cols] destination: the block at (dst_row_off, dst_col_off)
  * receives scale * src (src is [rows, cols]; transposed first when transpose != 0, i.e. the

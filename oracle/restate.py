@@ -75,13 +75,31 @@ def rms_layernorm_bwd(dY, X, W, r, gemma=False):
 # --------------------------------------------------------------------------------------
 
 
-def _rot(q1, q2, cos, sin):
-    # products and sums each round to the operand dtype, exactly as two separate
-    # tensor ops would (the reference's Triton may contract to FMA: see SURVEY 9)
-    return q1 * cos - q2 * sin, q2 * cos + q1 * sin
+# How the reference's `q0*cos - q1*sin` / `q1*cos + q0*sin` round (rope_embedding.py:82-83, 162-163):
+#   False  every product and the sum round to the operand dtype -- what TRITON_INTERPRET=1 (numpy)
+#          does; pins the fp32 / fp16 golden vectors generated in the build container;
+#   True   what Triton 3.6 emits NATIVELY on sm_100 (PTX read off the GPU box, profiles/
+#          r2_triton_rope_ptx.txt): `fma(q0, cos, -rn(q1*sin))` and `fma(q0, sin, rn(q1*cos))`,
+#          i.e. one product rounded and the other fused.  The GPU parity tests use this form.
+ROPE_NATIVE_CONTRACTION = False
 
 
-def rope_noindex(Q, cos, sin, backward=False):
+def _rot(q1, q2, cos, sin, contract=None):
+    contract = ROPE_NATIVE_CONTRACTION if contract is None else contract
+    dt = torch.promote_types(torch.promote_types(q1.dtype, cos.dtype), q2.dtype)
+    if not contract or dt == torch.float32:
+        # products and sums each round to the operand dtype, exactly as separate tensor ops would
+        return q1 * cos - q2 * sin, q2 * cos + q1 * sin
+    # 16-bit operands: a product of two 8/11-bit significands is exact in fp32
+    f = torch.float32
+    m_s = (q2 * sin).to(f)                      # rn16(q1*sin)
+    m_c = (q2 * cos).to(f)                      # rn16(q1*cos)
+    o1 = (q1.to(f) * cos.to(f) - m_s).to(dt)
+    o2 = (q1.to(f) * sin.to(f) + m_c).to(dt)
+    return o1, o2
+
+
+def rope_noindex(Q, cos, sin, backward=False, contract=None):
     """kernels/rope_embedding.py:104-166 (+ wrapper :169-261).
 
     Q: [B, S, n_heads, D] (contiguous).  cos/sin: [>=S, D]; only the first D/2 columns
@@ -96,11 +114,11 @@ def rope_noindex(Q, cos, sin, backward=False):
         sin1 = -sin1
     q1 = Q[..., :half].to(cos.dtype)
     q2 = Q[..., half:].to(cos.dtype)
-    o1, o2 = _rot(q1, q2, cos1, sin1)
+    o1, o2 = _rot(q1, q2, cos1, sin1, contract)
     return torch.cat([o1, o2], dim=-1).to(Q.dtype)
 
 
-def rope_qk(Q, K, cos, sin, indices=None, backward=False):
+def rope_qk(Q, K, cos, sin, indices=None, backward=False, contract=None):
     """kernels/rope_embedding.py:23-98 (+ wrapper :283-399).
 
     Q: [B, Hq, S, D], K: [B, Hk, S, D].  Row of cos/sin is `indices[b*S+s]` when given,
@@ -119,7 +137,7 @@ def rope_qk(Q, K, cos, sin, indices=None, backward=False):
 
     def one(T):
         t1, t2 = T[..., :half], T[..., half:]
-        o1, o2 = _rot(t1, t2, cos1, sin1)
+        o1, o2 = _rot(t1, t2, cos1, sin1, contract)
         return torch.cat([o1, o2], dim=-1).to(T.dtype)
 
     return one(Q), one(K)

@@ -168,6 +168,21 @@ def gemm(M, N, segs, n_segs, a_mn, b_mn, abdt, C, ldc, cdt, alpha, accumulate, s
     Cv.copy_(acc.to(_DT[cdt]))
 
 
+def gemm_grouped(probs, n_probs, abdt, scratch, stream):
+    """Sequential interpretation of a grouped launch: problems in list order, so every in-launch
+    dependency (wait_problem < own index) is already satisfied.  Checks the documented contract."""
+    for i in range(n_probs):
+        g = probs[i]
+        assert g.n_segs >= 1 and g.block_n in (64, 128, 256)
+        assert not (g.b_mn_major and g.block_n < 128)
+        if g.wait_problem >= 0:
+            assert g.wait_problem < i and probs[g.wait_problem].signals
+            assert 0 <= g.wait_segment < g.n_segs
+        assert g.split_k <= 1 or g.workspace
+        gemm(g.M, g.N, g.segs, g.n_segs, g.a_mn_major, g.b_mn_major, abdt, g.C, g.ldc, g.c_dtype, g.alpha,
+             g.accumulate, 1, None, g.block_n, 2, stream)
+
+
 def cast_pad_2d(src, sdt, sld, rows, cols, dst, ddt, dld, drows, dcols, roff, coff, scale, transpose,
                 stream):
     s = view2d(src, _DT[sdt], rows, cols, sld).double() * scale
@@ -208,7 +223,7 @@ _TABLE = {
     "ub200_add_rms_layernorm_fwd": add_rms_layernorm_fwd, "ub200_rms_layernorm_bwd_acc": rms_layernorm_bwd_acc,
     "ub200_rope_qk": rope_qk, "ub200_glu_fwd": glu_fwd, "ub200_glu_bwd": glu_bwd,
     "ub200_cross_entropy_fwd": cross_entropy_fwd, "ub200_cross_entropy_bwd": cross_entropy_bwd,
-    "ub200_dequantize_nf4": dequantize_nf4, "ub200_quantize_nf4": quantize_nf4, "ub200_gemm": gemm,
+    "ub200_dequantize_nf4": dequantize_nf4, "ub200_quantize_nf4": quantize_nf4, "ub200_gemm": gemm, "ub200_gemm_grouped": gemm_grouped,
     "ub200_cast_pad_2d": cast_pad_2d, "ub200_gemv_nf4": gemv_nf4,
     "ub200_gemv_dense": gemv_dense,
 }

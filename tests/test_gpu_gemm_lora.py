@@ -253,3 +253,80 @@ def test_fused_linear_ce_vs_oracle():
         assert abs(loss.item() - loss_r.item()) < 2e-3 * abs(loss_r.item()) + 1e-3
         e = (hg.grad.float().cpu() - dH_r.float()).abs().max().item()
         assert e < 2e-2 * dH_r.float().abs().max().item() + 1e-6, e
+
+
+# ---------------------------------------------------------------------------------------------
+# the shapes the BENCH runs (round-2 verdict item 2): lm_head chunk GEMM (501 N-tiles, raster
+# mode 1) and its MN-major dH twin, the N = 14336 / K = 14336 projections, split-K dA/dB at T = 8192
+# ---------------------------------------------------------------------------------------------
+def _check_rows(out, A, Bm, rows, b_is_kn, alpha=1.0, tol=6e-3):
+    """`out[rows]` against fp32 on sampled rows.  A [M,K]; Bm is [N,K] (or [K,N] if b_is_kn)."""
+    Bf = Bm.float()
+    ref = A[rows].float() @ (Bf if b_is_kn else Bf.t())
+    err = (out[rows].float() - alpha * ref).abs().max().item()
+    assert err <= tol * ref.abs().max().item() * abs(alpha) + 1e-6, err
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(2048, 128256, 4096, False), (2048, 4096, 128256, True),
+                                        (8192, 14336, 4096, False), (8192, 4096, 14336, False),
+                                        (8192, 4096, 14336, True), (8192, 1024, 4096, False)])
+def test_gemm_bench_shapes(M, N, K, b_mn):
+    from unsloth_b200.kernels.utils import gemm
+    torch.manual_seed(M + N)
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(BF)
+    Bm = (torch.randn(K, N, device=DEV) if b_mn else torch.randn(N, K, device=DEV)).mul_(0.05).to(BF)
+    out = torch.empty(M, N, device=DEV, dtype=BF)
+    gemm(M, N, [(A, Bm, K)], out, b_mn=b_mn)
+    rows = torch.arange(0, M, 97, device=DEV)
+    _check_rows(out, A, Bm, rows, b_mn)
+    # every column tile is covered: the last rows / columns and a few interior tiles
+    rows2 = torch.tensor([0, 127, 128, 255, 256, M - 1], device=DEV)
+    _check_rows(out, A, Bm, rows2, b_mn)
+    out2 = torch.empty_like(out)
+    gemm(M, N, [(A, Bm, K)], out2, b_mn=b_mn)
+    assert torch.equal(out, out2)                       # run-to-run bitwise
+
+
+@pytest.mark.parametrize("M,T_", [(14336, 8192), (4096, 8192), (1024, 8192)])
+def test_splitk_rank_block_reductions_at_cfg2(M, T_):
+    """dB_full[M, 64] = s * dY^T @ XA and dA^T[M, 64] = X^T @ G with both operands MN-major and a
+    split-K reduction over the T = 8192 tokens, the way fast_lora.py launches them."""
+    from unsloth_b200.kernels.fast_lora import _split_k
+    from unsloth_b200.kernels.utils import gemm
+    torch.manual_seed(M)
+    dY = (torch.randn(T_, M, device=DEV) * 0.1).to(BF)
+    XA = torch.zeros(T_, 64, device=DEV, dtype=BF)
+    XA[:, :16] = (torch.randn(T_, 16, device=DEV) * 0.3).to(BF)
+    out = torch.empty(M, 64, device=DEV, dtype=torch.float32)
+    sk = _split_k(M, 64, T_)
+    gemm(M, 64, [(dY, XA, T_)], out, a_mn=True, b_mn=True, alpha=2.0, split_k=sk)
+    ref = 2.0 * (dY.float().t() @ XA.float())
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (err, sk)
+    assert torch.count_nonzero(out[:, 16:]) == 0
+    out2 = torch.empty_like(out)
+    gemm(M, 64, [(dY, XA, T_)], out2, a_mn=True, b_mn=True, alpha=2.0, split_k=sk)
+    assert torch.equal(out, out2)
+
+
+def test_fused_ce_odd_vocab_and_trainable_head():
+    """V = 32001 (not a multiple of 8: the chunk buffer's row stride is padded for TMA) with a
+    trainable lm_head + bias against autograd on fp32 logits."""
+    from unsloth_b200.kernels import unsloth_fused_ce_loss
+    torch.manual_seed(8)
+    B, S, H, V = 2, 300, 512, 32001
+    hidden = (torch.randn(B, S, H, device=DEV)).to(BF)
+    Wlm = (torch.randn(V, H, device=DEV) * 0.05).to(BF)
+    bias = (torch.randn(V, device=DEV) * 0.1).to(BF)
+    labels = torch.randint(0, V, (B, S), device=DEV); labels[0, 5] = -100
+    hg, Wg, bg = hidden.clone().requires_grad_(), Wlm.clone().requires_grad_(), bias.clone().requires_grad_()
+    loss = unsloth_fused_ce_loss(None, hg * 1, Wg, bg, labels, None, None, None, chunk_rows=256)
+    loss.backward()
+    h32, W32, b32 = (t.float().clone().requires_grad_() for t in (hidden, Wlm, bias))
+    shift = torch.full_like(labels, -100); shift[:, :-1] = labels[:, 1:]
+    ref = torch.nn.functional.cross_entropy((h32 @ W32.t() + b32).view(-1, V), shift.view(-1), ignore_index=-100)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 3e-3 * abs(ref.item())
+    for n, a, b in (("dH", hg.grad, h32.grad), ("dW", Wg.grad, W32.grad), ("db", bg.grad, b32.grad)):
+        e = (a.float() - b).abs().max().item()
+        assert e < 3e-2 * b.abs().max().item() + 1e-7, (n, e)

@@ -168,8 +168,9 @@ def test_rope_bf16_vs_oracle_inplace_strided(D, Hq, Hk, tdt):
     cos, sin = _tables(128, D, dtype=tdt)
     qbuf = torch.randn(B, S, Hq * D).to(torch.bfloat16)
     kbuf = torch.randn(B, S, Hk * D).to(torch.bfloat16)
-    Qr = R.rope_noindex(qbuf.view(B, S, Hq, D), cos, sin).transpose(1, 2)
-    Kr = R.rope_noindex(kbuf.view(B, S, Hk, D), cos, sin).transpose(1, 2)
+    # native-Triton rounding (one product rounded, the other fused): oracle/restate.py::_rot
+    Qr = R.rope_noindex(qbuf.view(B, S, Hq, D), cos, sin, contract=True).transpose(1, 2)
+    Kr = R.rope_noindex(kbuf.view(B, S, Hk, D), cos, sin, contract=True).transpose(1, 2)
     qg, kg = qbuf.to(DEV), kbuf.to(DEV)
     Q = qg.view(B, S, Hq, D).transpose(1, 2)
     K = kg.view(B, S, Hk, D).transpose(1, 2)
@@ -179,7 +180,7 @@ def test_rope_bf16_vs_oracle_inplace_strided(D, Hq, Hk, tdt):
     # indices path == explicit positions; round trip fwd -> bwd restores the input (rotation)
     idx = torch.randint(0, 128, (B * S,), dtype=torch.int32)
     Q2r, K2r = R.rope_qk(qbuf.view(B, S, Hq, D).transpose(1, 2), kbuf.view(B, S, Hk, D).transpose(1, 2),
-                         cos, sin, idx)
+                         cos, sin, idx, contract=True)
     qg2, kg2 = qbuf.to(DEV), kbuf.to(DEV)
     Q2, K2 = fast_rope_embedding(qg2.view(B, S, Hq, D).transpose(1, 2),
                                  kg2.view(B, S, Hk, D).transpose(1, 2), cos.to(DEV), sin.to(DEV),

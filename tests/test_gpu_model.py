@@ -300,3 +300,47 @@ def test_cuda_graph_step_matches_eager():
     assert max(abs(a - b) for a, b in zip(le, lg)) < 2e-3, (le, lg)
     assert (pe - pg).abs().max() < 1e-4
     assert lg[0] != lg[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# REAL widths (round-2 verdict item 2): one decoder layer of the actual BASELINE architectures
+# (H=4096 / D=128 / I=14336; Gemma-2 H=3584 / D=256; Mistral with a live sliding window) against
+# the fp32 CPU HF path.  vocab is cut to 4096 only to keep the CPU reference's lm_head small.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,extra,seq", [
+    ("llama-3-8b", {}, 256),
+    ("mistral-7b-v0.3", {"sliding_window": 96}, 256),
+    ("gemma-2-9b", {"sliding_window": 128}, 256),
+])
+def test_real_width_single_layer_matches_reference_cpu_path(name, extra, seq):
+    from unsloth_b200.patch import build_qlora_model, hf_config
+    from unsloth_b200.kernels import get_lora_parameters
+    kw = dict(vocab_size=4096, **extra)
+    model = build_qlora_model(name, r=16, lora_alpha=16, device=DEV, num_hidden_layers=1, init_b_std=0.02, **kw)
+    ref_kw = dict(kw)
+    if "sliding_window" in ref_kw:
+        ref_kw["sliding_window"] += 1      # the reference's window_size=(sw, sw) keeps sw + 1 keys (mistral.py:112-128)
+    ref = _reference_from(model, hf_config(name, 1, **ref_kw))
+    torch.manual_seed(1)
+    ids = torch.randint(0, 4096, (2, seq))
+    labels = ids.clone(); labels[0, :5] = -100
+    out = model(input_ids=ids.to(DEV), labels=labels.to(DEV))
+    out.loss.backward()
+    ref_out = ref(input_ids=ids, labels=labels)
+    ref_out.loss.backward()
+    rel = abs(out.loss.item() - ref_out.loss.item()) / abs(ref_out.loss.item())
+    worst, worst_ratio = 1.0, 0.0
+    lo, lr = model.model.layers[0], ref.model.layers[0]
+    for po, pr in ((lo.self_attn, lr.self_attn), (lo.mlp, lr.mlp)):
+        for pn in ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"):
+            _, _, A, B, _ = get_lora_parameters(getattr(po, pn))
+            for ours, theirs in ((A.grad, getattr(pr, pn).A.grad), (B.grad, getattr(pr, pn).B.grad)):
+                a, b = ours.float().cpu().flatten(), theirs.flatten()
+                cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+                worst = min(worst, cos)
+                worst_ratio = max(worst_ratio, abs(a.norm().item() / (b.norm().item() + 1e-30) - 1))
+    print("REALWIDTH %s: loss rel err %.2e, worst LoRA-grad cosine %.5f, worst norm ratio err %.3f"
+          % (name, rel, worst, worst_ratio))
+    assert rel <= 5e-3, rel
+    assert worst > 0.995, worst
+    assert worst_ratio < 0.05, worst_ratio

@@ -136,15 +136,16 @@ def _tables(S, D, base, dtype):
 
 
 @pytest.mark.parametrize("indexed", [False, True])
-@pytest.mark.parametrize("B,S,Hq,Hk,D,tdt", [(4, 2048, 32, 8, 128, BF), (1, 4096, 16, 8, 256, torch.float32)])
-def test_rope_vs_reference(refk, indexed, B, S, Hq, Hk, D, tdt):
+@pytest.mark.parametrize("B,S,Hq,Hk,D,tdt,adt", [(4, 2048, 32, 8, 128, BF, BF), (1, 4096, 16, 8, 256, torch.float32, BF),
+                                                  (2, 1024, 32, 8, 128, torch.float16, torch.float16)])
+def test_rope_vs_reference(refk, indexed, B, S, Hq, Hk, D, tdt, adt):
     from unsloth_b200.kernels import fast_rope_embedding
     torch.manual_seed(7)
     cos, sin = _tables(S, D, 500000.0, tdt)
-    q0 = torch.randn(B, S, Hq * D, device=DEV).to(BF)
-    k0 = torch.randn(B, S, Hk * D, device=DEV).to(BF)
-    dq = torch.randn(B, Hq, S, D, device=DEV).to(BF)
-    dk = torch.randn(B, Hk, S, D, device=DEV).to(BF)
+    q0 = torch.randn(B, S, Hq * D, device=DEV).to(adt)
+    k0 = torch.randn(B, S, Hk * D, device=DEV).to(adt)
+    dq = torch.randn(B, Hq, S, D, device=DEV).to(adt)
+    dk = torch.randn(B, Hk, S, D, device=DEV).to(adt)
     idx = None
     if indexed:        # packed-style position ids: two documents per row
         pos = torch.cat([torch.arange(S // 3), torch.arange(S - S // 3)]).repeat(B)
@@ -160,7 +161,7 @@ def test_rope_vs_reference(refk, indexed, B, S, Hq, Hk, D, tdt):
         return Qc, Kc, qb.grad, kb.grad
     r = run(refk.rope_embedding.fast_rope_embedding)
     o = run(fast_rope_embedding)
-    tag = "rope_%s_D%d" % ("indexed" if indexed else "noindex", D)
+    tag = "rope_%s_D%d_%s" % ("indexed" if indexed else "noindex", D, str(adt).split(".")[-1])
     for n, a, b in zip(("Q", "K", "dQ", "dK"), o, r):
         gate_elementwise(tag + ":" + n, a.contiguous(), b.contiguous())
 

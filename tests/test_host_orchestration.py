@@ -22,7 +22,8 @@ def gemm_double(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=F
                 block_n=0, cta_group=0):
     """out[M,N] (+)= alpha * sum_s A_s . B_s^T ; a_mn: A stored [K,M]; b_mn: B stored [K,N]."""
     acc = torch.zeros(M, N, dtype=torch.float64)
-    for A, B, K in segs:
+    for sg in segs:
+        A, B, K = sg[0], sg[1], sg[2]
         assert A.dim() == 2 and B.dim() == 2 and A.stride(-1) == 1 and B.stride(-1) == 1
         Am = A.t() if a_mn else A
         Bm = B.t() if b_mn else B
@@ -36,6 +37,20 @@ def gemm_double(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=F
     return out
 
 
+def gemm_grouped_double(problems):
+    """Documented semantics of ub200_gemm_grouped: the problems in list order (a dependency may only
+    point at an EARLIER problem that signals; the dependent operand must be that problem's output)."""
+    for i, pr in enumerate(problems):
+        if pr.wait is not None:
+            dep, seg, whole = pr.wait
+            assert 0 <= dep < i and problems[dep].signals and 0 <= seg < len(pr.segs)
+            operand = pr.segs[seg][1] if whole else pr.segs[seg][0]
+            assert operand.data_ptr() == problems[dep].out.data_ptr()
+        assert not (pr.b_mn and pr.block_n < 128)
+        gemm_double(pr.M, pr.N, pr.segs, pr.out, pr.a_mn, pr.b_mn, pr.alpha, pr.accumulate)
+    return [pr.out for pr in problems]
+
+
 def cast_pad_double(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
     blk = (src.t() if transpose else src).to(torch.float64) * scale
     dst.zero_()
@@ -43,15 +58,17 @@ def cast_pad_double(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
     return dst
 
 
-@pytest.fixture
-def host_doubles(monkeypatch):
+@pytest.fixture(params=["grouped", "per-gemm"])
+def host_doubles(monkeypatch, request):
     import unsloth_b200._lib as L
+    monkeypatch.setenv("UB200_GROUPED", "1" if request.param == "grouped" else "0")
     import unsloth_b200.kernels.fast_lora as FL
     import unsloth_b200.kernels.utils as KU
     monkeypatch.setattr(L, "require_cuda", lambda *a, **k: None)
     for mod in (FL, KU):
         monkeypatch.setattr(mod, "gemm", gemm_double)
         monkeypatch.setattr(mod, "cast_pad", cast_pad_double)
+        monkeypatch.setattr(mod, "gemm_grouped", gemm_grouped_double)
     KU.set_keep_dequant(False)
     yield FL
     KU.set_keep_dequant(None)
@@ -119,35 +136,3 @@ def test_lora_without_adapters(golden, host_doubles):
     _close(O, T(g["X"]) @ T(g["oW"]).t())
     O.backward(T(g["dY"]).clone())
     _close(X.grad, T(g["dY"]) @ T(g["oW"]))
-
-
-def test_side_stream_variant_takes_the_same_arithmetic_path(golden, host_doubles, monkeypatch):
-    """UB200_SKINNY_STREAMS=1 (experimental fork/join of the dB GEMMs onto a side stream): with the
-    stream objects replaced by recording fakes the results are unchanged and the fork / join calls
-    are balanced (every fork waits on the main stream first, the main stream waits for the side
-    stream before the gradients are used)."""
-    import contextlib
-    FL = host_doubles
-    log = []
-
-    class FakeStream:
-        def __init__(self, name):
-            self.name = name
-
-        def wait_stream(self, other):
-            log.append((self.name, "waits", other.name))
-    main, side = FakeStream("main"), FakeStream("side")
-    monkeypatch.setattr(FL, "_side_stream", lambda dev: side)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: main)
-    monkeypatch.setattr(torch.cuda, "stream", lambda st: contextlib.nullcontext())
-    g = golden("lora_qkv")
-    s = float(g["s"])
-    X = T(g["X"]).clone().requires_grad_()
-    P = {n: _param(g[n]) for n in ("qA", "qB", "kA", "kB", "vA", "vB")}
-    Q, K, V = FL.LoRA_QKV.apply(X, T(g["qW"]), None, P["qA"], P["qB"], s, T(g["kW"]), None, P["kA"], P["kB"], s,
-                                T(g["vW"]), None, P["vA"], P["vB"], s, False)
-    torch.autograd.backward([Q, K, V], [T(g["dQ"]).clone(), T(g["dK"]).clone(), T(g["dV"]).clone()])
-    _close(X.grad, g["dX"])
-    for n in ("q", "k", "v"):
-        _close(P[n + "A"].grad, g["d_%sA" % n]); _close(P[n + "B"].grad, g["d_%sB" % n])
-    assert log == [("side", "waits", "main"), ("main", "waits", "side")]

@@ -32,6 +32,17 @@ class GemmSegment(Structure):
                 ("k", c_int64)]
 
 
+class GemmProblem(Structure):
+    _fields_ = [("M", c_int), ("N", c_int), ("segs", POINTER(GemmSegment)), ("n_segs", c_int),
+                ("a_mn_major", c_int), ("b_mn_major", c_int), ("C", c_void_p), ("ldc", c_int64),
+                ("c_dtype", c_int), ("alpha", c_float), ("accumulate", c_int), ("split_k", c_int),
+                ("workspace", c_void_p), ("block_n", c_int), ("signals", c_int),
+                ("wait_problem", c_int), ("wait_segment", c_int), ("wait_all", c_int)]
+
+
+GROUPED_MAX_PROBLEMS, GROUPED_MAX_SEGMENTS = 8, 4
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         # build in-tree when a compiler is around (developer box); never fall back to CPU code
@@ -73,6 +84,8 @@ _SIGS = {
     "ub200_gemm": ([_i, _i, POINTER(GemmSegment), _i, _i, _i, _i, _p, _l, _i, _f, _i, _i, _p, _i,
                     _i, _p], c_int),
     "ub200_gemm_workspace_bytes": ([_i, _i, _i, POINTER(c_int64)], c_int),
+    "ub200_gemm_grouped": ([POINTER(GemmProblem), _i, _i, _p, _p], c_int),
+    "ub200_gemm_grouped_scratch_ints": ([POINTER(GemmProblem), _i, POINTER(c_int)], c_int),
     "ub200_cast_pad_2d": ([_p, _i, _l, _i, _i, _p, _i, _l, _i, _i, _i, _i, _f, _i, _p], c_int),
     "ub200_adamw_flat": ([_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _f, _p], c_int),
 }

@@ -16,18 +16,19 @@
 //   2*(Hq+Hk)*D*bytes (read+write) + D*table_bytes (first halves of cos and sin).
 //
 // `compute_dtype` reproduces the reference's rounding: the no-index
-// kernel evaluates in the TABLE dtype, the QK kernel in the promoted dtype; each product
-// and the sum round to that dtype.
+// kernel evaluates in the TABLE dtype, the QK kernel in the promoted dtype.  Within that dtype
+// the roundings fall where the reference's natively compiled Triton kernel puts them (one product
+// rounded, the other fused into the sum by fma) -- measured on a B200, not assumed.
 #include <cstdlib>
 
 #include "common.cuh"
 
 // default rounding modes of the packed 16-bit kernel (see rope_packed_kernel)
 #ifndef UB200_ROPE_MODE_BF16
-#define UB200_ROPE_MODE_BF16 0
+#define UB200_ROPE_MODE_BF16 4
 #endif
 #ifndef UB200_ROPE_MODE_F16
-#define UB200_ROPE_MODE_F16 0
+#define UB200_ROPE_MODE_F16 4
 #endif
 
 namespace ub {
@@ -70,12 +71,12 @@ __global__ void __launch_bounds__(512) rope_kernel(
       for (int i = 0; i < V; ++i) {
         const float a1 = round_to(comp_dt, x1[i]), a2 = round_to(comp_dt, x2[i]);
         // q1*cos - q2*sin ; q2*cos + q1*sin, each op rounded to the compute dtype
-        const float m11 = round_to(comp_dt, __fmul_rn(a1, c[i]));
+        // the contraction LLVM applies to the reference kernel (see rope_packed_kernel, MODE 4):
+        // second product rounded, first one fused into the sum
         const float m22 = round_to(comp_dt, __fmul_rn(a2, sn[i]));
         const float m21 = round_to(comp_dt, __fmul_rn(a2, c[i]));
-        const float m12 = round_to(comp_dt, __fmul_rn(a1, sn[i]));
-        o1[i] = round_to(comp_dt, __fsub_rn(m11, m22));
-        o2[i] = round_to(comp_dt, __fadd_rn(m21, m12));
+        o1[i] = round_to(comp_dt, __fmaf_rn(a1, c[i], -m22));
+        o2[i] = round_to(comp_dt, __fmaf_rn(a1, sn[i], m21));
       }
       store_vec<T>(p + d0, o1);
       store_vec<T>(p + half + d0, o2);
@@ -108,6 +109,9 @@ template <> struct Pk2<__half> {
 //   1  LLVM's fp-contract=fast form of `a*c - b*s`:  fma(a, c, -rn(b*s)) ; fma(b, c, rn(a*s))
 //   2  the other contraction:                        fma(-b, s, rn(a*c)) ; fma(a, s, rn(b*c))
 //   3  fp32 evaluation, one rounding at the store
+//   4  what Triton 3.6 / LLVM emits for the reference kernel on sm_100 (read off its PTX,
+//      profiles/r2_triton_rope_ptx.txt):  o1 = fma(a, c, -rn(b*s)) ; o2 = fma(a, s, rn(b*c))
+//      -- bit-identical to the reference's native bf16 AND fp16 output (the DEFAULT)
 template <typename T, int HP, int MODE>
 __global__ void __launch_bounds__(512) rope_packed_kernel(
     T* Q, int64_t q_bs, int64_t q_hs, int64_t q_ss, T* K, int64_t k_bs, int64_t k_hs,
@@ -164,6 +168,9 @@ __global__ void __launch_bounds__(512) rope_packed_kernel(
             o2.h[i] = __hfma2(x2[u].h[i], c.h[i], __hmul2_rn(x1[u].h[i], sn.h[i]));
           } else if (MODE == 2) {
             o1.h[i] = __hfma2(__hneg2(x2[u].h[i]), sn.h[i], __hmul2_rn(x1[u].h[i], c.h[i]));
+            o2.h[i] = __hfma2(x1[u].h[i], sn.h[i], __hmul2_rn(x2[u].h[i], c.h[i]));
+          } else if (MODE == 4) {
+            o1.h[i] = __hfma2(x1[u].h[i], c.h[i], __hneg2(__hmul2_rn(x2[u].h[i], sn.h[i])));
             o2.h[i] = __hfma2(x1[u].h[i], sn.h[i], __hmul2_rn(x2[u].h[i], c.h[i]));
           } else {
             const float2 a = Pk2<T>::to_f2(x1[u].h[i]), b = Pk2<T>::to_f2(x2[u].h[i]);
@@ -229,7 +236,7 @@ extern "C" int ub200_rope_qk(void* Q, int64_t q_batch_stride, int64_t q_head_str
       n_heads_q, n_heads_k, head_dim, backward, n_rows)
 #define GOM(T)                                                                                      \
   do {                                                                                              \
-    if (mode == 1) GOP(T, 1); else if (mode == 2) GOP(T, 2); else if (mode == 3) GOP(T, 3); else GOP(T, 0); \
+    if (mode == 1) GOP(T, 1); else if (mode == 2) GOP(T, 2); else if (mode == 3) GOP(T, 3); else if (mode == 0) GOP(T, 0); else GOP(T, 4); \
   } while (0)
     if (dtype == UB200_BF16) GOM(__nv_bfloat16);
     else GOM(__half);

@@ -22,7 +22,7 @@ import os
 import torch
 
 from .. import _lib as L
-from .utils import (GradModeAware, RANK_BLOCK, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
+from .utils import (GradModeAware, Problem, RANK_BLOCK, gemm_grouped, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
                     keep_dequant, keep_for_backward, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
                     matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
@@ -31,21 +31,16 @@ from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
 
 _SM = 148
 
-# EXPERIMENTAL (default off; written after the round-1 GPU budget was spent, not yet run on
-# hardware): the rank-block GEMMs of a backward (dB_i = s dY_i^T XA, N = 64, 64-128 CTAs each) do
-# not depend on G / dA / dX, so they can run on a side stream next to the other skinny GEMMs and
-# fill the SMs those leave idle.  Fork/join with events, so it is capturable in the step's CUDA
-# graph (parallel branches).  UB200_SKINNY_STREAMS=1 turns it on.
-_SIDE_STREAMS = {}
+def _grouped():
+    """UB200_GROUPED=0 falls back to one launch per GEMM (round-1 schedule; A/B measurements)."""
+    return os.environ.get("UB200_GROUPED", "1") != "0"
 
 
-def _side_stream(device):
-    if os.environ.get("UB200_SKINNY_STREAMS", "0") != "1":
-        return None
-    st = _SIDE_STREAMS.get(device.index)
-    if st is None:
-        st = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
-    return st
+def _split_k_grouped(T):
+    """Split factor of the token reductions (dA / dB) inside a grouped launch: ~32 k-blocks (2048
+    tokens) per work item, so the items are short enough to fill the tail of the launch."""
+    kb = (T + 63) // 64
+    return max(1, min(16, kb // 32))
 
 
 def _epoch():
@@ -127,6 +122,8 @@ class _Group:
     def forward(self, keep=False):
         """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None.  `keep`: the
         dequantised weights are private tensors left in `self.dense` for the backward."""
+        if _grouped():
+            return self._forward_grouped(keep)
         X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
         if keep:
             self.dense = []
@@ -155,15 +152,125 @@ class _Group:
             outs.append(Y)
         return outs, XA
 
+    # ---- grouped execution: ONE persistent launch per phase (csrc/gemm_grouped.cu) ---------------
+    def _forward_grouped(self, keep):
+        X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
+        if keep:
+            self.dense = []
+        probs, XA = [], None
+        r_true = self.rank_total
+        if self.has_lora:
+            XA = torch.empty((T, self.Rp), dtype=dt, device=dev)
+            probs.append(Problem(T, self.Rp, [(X2, self.A_cat(refresh=True), self.in_f)], XA,
+                                 signals=True, tag="rank"))
+        outs = []
+        for off, (W, Wq, A, B, s) in zip(self.offs, self.projs):
+            Wd = dense_weight(W, Wq, dt, len(outs), fresh=keep)
+            if keep:
+                self.dense.append(Wd if Wq is not None else None)
+            Bop, b_mn = as_b_operand(Wd)
+            N = Wd.shape[0]
+            segs = [(X2, Bop, self.in_f)]
+            wait = None
+            if A is not None:
+                Bc = B if B.stride(-1) == 1 else B.contiguous()
+                if b_mn:
+                    B_pad = cached_cast_pad(Bc, (self.Rp, N), dt, row_off=off, scale=s, transpose=True,
+                                            refresh=True)
+                else:
+                    B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s, refresh=True)
+                segs.append((XA, B_pad, self.Rp, A.shape[0]))
+                wait = (0, 1, False)
+            Y = torch.empty((T, N), dtype=dt, device=dev)
+            probs.append(Problem(T, N, segs, Y, b_mn=b_mn, wait=wait))
+            outs.append(Y)
+        gemm_grouped(probs)
+        return outs, XA
+
+    def backward_problems(self, dYs, XA, dX_out=None, need_dX=True, extra_front=(), extra_mid=()):
+        """The problems of this group's backward as ONE list (producer G first):
+            G = sum_i dY_i @ (s_i B_i)            [T, Rp]   rank block, signals
+            dB_i = s_i dY_i^T @ XA                [out_i, Rp] fp32, split-K over tokens
+            (extra_mid: problems of a neighbouring group that ride in the same launch)
+            dX = sum_i dY_i @ W_i + G @ A_cat     waits for its row block of G
+            dA_cat^T = X^T @ G                    [in, Rp] fp32, split-K, waits for all of G
+        Returns (problems, finish) where finish() -> (dX or None, [(dA_i, dB_i)...])."""
+        X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
+        probs = list(extra_front)
+        g_idx = None
+        G = dA_catT = None
+        dB_fulls = []
+        sk = _split_k_grouped(T)
+        if self.has_lora:
+            segs = []
+            for off, dY, (W, Wq, A, B, s) in zip(self.offs, dYs, self.projs):
+                if A is None:
+                    continue
+                Bc = B if B.stride(-1) == 1 else B.contiguous()
+                out_f = Bc.shape[0]
+                B_pad = cached_cast_pad(Bc, (out_f, Rp), dt, col_off=off, scale=s)
+                segs.append((dY, B_pad, out_f))
+            G = torch.empty((T, Rp), dtype=dt, device=dev)
+            g_idx = len(probs)
+            # several segments of G may exceed the per-problem limit only with > 4 adapters per group
+            probs.append(Problem(T, Rp, segs, G, b_mn=True, signals=True, tag="rank"))
+            for dY, (W, Wq, A, B, s) in zip(dYs, self.projs):
+                if A is None:
+                    dB_fulls.append(None)
+                    continue
+                out_f = dY.shape[1]
+                dB_full = torch.empty((out_f, Rp), dtype=torch.float32, device=dev)
+                probs.append(Problem(out_f, Rp, [(dY, XA, T)], dB_full, a_mn=True, b_mn=True, alpha=s,
+                                     split_k=sk, tag="rank"))
+                dB_fulls.append(dB_full)
+        probs.extend(extra_mid)
+        dX = None
+        if need_dX:
+            segs = []
+            kept = self.dense if self.dense is not None else [None] * len(self.projs)
+            for slot, (dY, (W, Wq, A, B, s)) in enumerate(zip(dYs, self.projs)):
+                Wd = kept[slot] if kept[slot] is not None else dense_weight(W, Wq, dt, slot)   # [out, in]
+                Bop, b_mn = as_b_operand(Wd.t())
+                if not b_mn:
+                    Bop, b_mn = Bop.t().contiguous(), True
+                segs.append((dY, Bop, dY.shape[1]))
+            wait = None
+            if self.has_lora:
+                segs.append((G, self.A_cat(), Rp, self.rank_total))
+                wait = (g_idx, len(segs) - 1, False)
+            # dA = X^T @ G reads X in the SAME launch, so dX cannot be written over the saved X buffer
+            # (the reference's inplace=True is a memory optimisation, fast_lora.py:194, 498; the
+            # 67 MB it saves is transient here)
+            inplace_ok = dX_out is not None and not self.has_lora
+            dX = dX_out if inplace_ok else torch.empty((T, self.in_f), dtype=dt, device=dev)
+            probs.append(Problem(T, self.in_f, segs, dX, b_mn=True, wait=wait))
+        if self.has_lora:
+            dA_catT = torch.empty((self.in_f, Rp), dtype=torch.float32, device=dev)
+            probs.append(Problem(self.in_f, Rp, [(X2, G, T)], dA_catT, a_mn=True, b_mn=True, split_k=sk,
+                                 wait=(g_idx, 0, True), tag="rank"))
+
+        def finish():
+            grads = []
+            for off, dB_full, (W, Wq, A, B, s) in zip(self.offs, dB_fulls or [None] * len(self.projs), self.projs):
+                if A is None:
+                    grads.append((None, None))
+                    continue
+                r = A.shape[0]
+                grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
+            return dX, grads
+        return probs, finish
+
     def backward(self, dYs, XA, dX_out=None, need_dX=True):
         """dYs: list of [T, out_i].  Returns (dX [T,in] or None, [(dA_i, dB_i) or (None, None)])."""
+        if _grouped():
+            probs, finish = self.backward_problems(dYs, XA, dX_out, need_dX)
+            if probs:
+                gemm_grouped(probs)
+            return finish()
         X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
         grads = []
         G = None
         if self.has_lora:
-            side = _side_stream(dev)
-            if side is not None:
-                side.wait_stream(torch.cuda.current_stream())       # fork: dYs / XA are ready here
             # dB_i [out, Rp] = s_i * dY_i^T @ XA ; keep this adapter's columns.  Independent of G.
             def _dBs():
                 res = []
@@ -178,9 +285,6 @@ class _Group:
                     res.append(dB_full)
                 return res
             dB_fulls = None
-            if side is not None:
-                with torch.cuda.stream(side):
-                    dB_fulls = _dBs()
             # G[T, Rp] = sum_i dY_i @ (s_i B_i) placed at the adapter's rank slot.  The B operand
             # is the SAME zero-padded [out_i, Rp] block the forward used, consumed MN-major
             # ([K=out_i, N=Rp] row-major): no transposed copy of B is ever made.
@@ -199,8 +303,6 @@ class _Group:
                  split_k=_split_k(self.in_f, Rp, T))
             if dB_fulls is None:
                 dB_fulls = _dBs()
-            if side is not None:
-                torch.cuda.current_stream().wait_stream(side)
             for off, dY, dB_full, (W, Wq, A, B, s) in zip(self.offs, dYs, dB_fulls, self.projs):
                 if A is None:
                     grads.append((None, None))
@@ -271,6 +373,8 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
         dY2 = _as2d(dY)
         T = X2.shape[0]
         dt, dev = X2.dtype, X2.device
+        if _grouped():
+            return LoRA_MLP._backward_grouped(ctx, dY2, X2, e, g, XA1, XA2)
         # --- down projection: DW = dY @ W_down + (dY @ s B_down) @ A_down          (:155)
         # `h` is not needed yet: a group over a placeholder input gives DW and G_down
         down = _Group(e, [(downW, downW_quant, downA, downB, downS)])  # in_f = I (e is [T, I])
@@ -315,6 +419,66 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
             [de, df], XA1, dX_out=X2 if ctx.inplace else None)
         return (dX.view(ctx.shape), None, None, d_gateA, d_gateB, None, None, None, d_upA, d_upB,
                 None, None, None, d_downA, d_downB, None, None, None, None)
+
+
+def _mlp_backward_grouped(ctx, dY2, X2, e, g, XA1, XA2):
+    """LoRA_MLP.backward (fast_lora.py:116-229) as TWO persistent launches around the in-place
+    activation backward:
+      A: G_down = dY @ sB_down | DW = dY @ W_down + G_down @ A_down | dB_down = s dY^T @ XA2
+      (swiglu / geglu backward in place: DW <- h, e <- df, g <- de)
+      B: G = de @ sB_gate + df @ sB_up | dB_gate, dB_up | dA_down^T = h^T @ G_down |
+         dX = de @ W_gate + df @ W_up + G @ A_cat | dA_cat^T = X^T @ G"""
+    (gateW, gateW_quant, gateS, upW, upW_quant, upS, downW, downW_quant, downS,
+     _backward_function) = ctx.custom_saved_tensors
+    gateA, gateB, upA, upB, downA, downB = ctx.lora
+    T = X2.shape[0]
+    dt, dev = X2.dtype, X2.device
+    I, Hout = e.shape[1], dY2.shape[1]
+    down = _Group(e, [(downW, downW_quant, downA, downB, downS)])
+    dense_gu, dense_down = ctx.dense
+    ctx.dense = None
+    Wd = dense_down[0] if dense_down is not None and dense_down[0] is not None else \
+        dense_weight(downW, downW_quant, dt, 0)                    # [H, I]
+    dense_down = None
+    Bop, b_mn = as_b_operand(Wd.t())
+    if not b_mn:
+        Bop, b_mn = Bop.t().contiguous(), True
+    sk = _split_k_grouped(T)
+    probs, G_down, dB_full = [], None, None
+    segs, wait = [(dY2, Bop, Hout)], None
+    if downA is not None:
+        Bc = downB if downB.stride(-1) == 1 else downB.contiguous()
+        B_pad = cached_cast_pad(Bc, (Bc.shape[0], down.Rp), dt, scale=downS)     # as in forward
+        G_down = torch.empty((T, down.Rp), dtype=dt, device=dev)
+        probs.append(Problem(T, down.Rp, [(dY2, B_pad, Bc.shape[0])], G_down, b_mn=True, signals=True, tag="rank"))
+        segs.append((G_down, down.A_cat(), down.Rp, downA.shape[0]))
+        wait = (0, 1, False)
+    DW = torch.empty((T, I), dtype=dt, device=dev)
+    probs.append(Problem(T, I, segs, DW, b_mn=True, wait=wait))
+    if downA is not None:
+        dB_full = torch.empty((Hout, down.Rp), dtype=torch.float32, device=dev)
+        probs.append(Problem(Hout, down.Rp, [(dY2, XA2, T)], dB_full, a_mn=True, b_mn=True, alpha=downS,
+                             split_k=sk, tag="rank"))
+    gemm_grouped(probs)
+    h, df, de = _backward_function(DW, e, g)                       # in place            (:156-157)
+    extra, dA_T = [], None
+    if downA is not None:
+        dA_T = torch.empty((I, down.Rp), dtype=torch.float32, device=dev)
+        extra = [Problem(I, down.Rp, [(h, G_down, T)], dA_T, a_mn=True, b_mn=True, split_k=sk, tag="rank")]
+    grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
+    grp.dense = dense_gu
+    probs, finish = grp.backward_problems([de, df], XA1, dX_out=X2 if ctx.inplace else None, extra_mid=extra)
+    gemm_grouped(probs)
+    dX, ((d_gateA, d_gateB), (d_upA, d_upB)) = finish()
+    d_downA = d_downB = None
+    if downA is not None:
+        r = downA.shape[0]
+        d_downA, d_downB = dA_T[:, :r].t(), dB_full[:, :r]
+    return (dX.view(ctx.shape), None, None, d_gateA, d_gateB, None, None, None, d_upA, d_upB,
+            None, None, None, d_downA, d_downB, None, None, None, None)
+
+
+LoRA_MLP._backward_grouped = staticmethod(_mlp_backward_grouped)
 
 
 def apply_lora_mlp_swiglu(self, X, inplace=True):

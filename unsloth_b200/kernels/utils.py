@@ -193,7 +193,8 @@ def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, s
     n = len(segs)
     arr = (L.GemmSegment * n)()
     ab_dtype = segs[0][0].dtype
-    for i, (A, B, K) in enumerate(segs):
+    for i, sg in enumerate(segs):
+        A, B, K = sg[0], sg[1], sg[2]
         _check_operand(A); _check_operand(B)
         if A.dtype != ab_dtype or B.dtype != ab_dtype:
             raise RuntimeError("unsloth_b200.gemm: mixed operand dtypes %s/%s" % (A.dtype, B.dtype))
@@ -212,8 +213,109 @@ def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, s
            int(block_n), int(cta_group), L.stream())
     if ev is not None:
         e1.record()
-        ev.append((2.0 * M * N * sum(k for _, _, k in segs), e0, e1))
+        bn = block_n or (256 if N > 128 else (128 if N > 64 else 64))
+        pair = cta_group == 2 or (cta_group == 0 and bn >= 128 and M > 128)
+        ev.append((2.0 * M * N * sum(sg[3] if len(sg) > 3 else sg[2] for sg in segs), e0, e1,
+                   {"kernel": "gemm2" if pair else "gemm1"}))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# grouped GEMM: one persistent launch for a list of dependent problems (csrc/gemm_grouped.cu)
+# ---------------------------------------------------------------------------------------------
+class Problem:
+    """One problem of a grouped launch: out[M,N] (+)= alpha * sum_s A_s . B_s^T.
+    segs: (A, B, K) or (A, B, K, K_true) -- K_true is the algorithmic reduction length (the LoRA
+    rank for a zero-padded rank block), used only for flop accounting.
+    wait: None or (index of an earlier problem whose output this one reads, first segment that
+    reads it, whole_output: bool)."""
+    __slots__ = ("M", "N", "segs", "out", "a_mn", "b_mn", "alpha", "accumulate", "split_k", "block_n",
+                 "signals", "wait", "tag")
+
+    def __init__(self, M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, split_k=1,
+                 block_n=0, signals=False, wait=None, tag="dense"):
+        self.M, self.N, self.segs, self.out = M, N, segs, out
+        self.a_mn, self.b_mn, self.alpha, self.accumulate = a_mn, b_mn, alpha, accumulate
+        self.split_k, self.signals, self.wait, self.tag = split_k, signals, wait, tag
+        if block_n == 0:
+            block_n = 256 if N > 128 else (128 if (N > 64 or b_mn) else 64)
+        self.block_n = block_n
+
+    def flops(self):
+        return 2.0 * self.M * self.N * sum((s[3] if len(s) > 3 else s[2]) for s in self.segs)
+
+
+_GROUP_SCRATCH = {}
+_GROUP_SCRATCH_INTS = 1 << 16
+
+
+def _group_scratch(device):
+    """Zero-initialised int32 scratch per (device, stream): the kernel leaves it zero again."""
+    st = L.stream()
+    key = (device.type, device.index, getattr(st, "value", None))
+    buf = _GROUP_SCRATCH.get(key)
+    if buf is None:
+        buf = _GROUP_SCRATCH[key] = torch.zeros(_GROUP_SCRATCH_INTS, dtype=torch.int32, device=device)
+    return buf
+
+
+def gemm_grouped(problems):
+    """Run `problems` (list of Problem, dependency producers first) in ONE persistent tcgen05 launch."""
+    n = len(problems)
+    if n > L.GROUPED_MAX_PROBLEMS:
+        raise RuntimeError("unsloth_b200.gemm_grouped: at most %d problems per launch" % L.GROUPED_MAX_PROBLEMS)
+    arr = (L.GemmProblem * n)()
+    keep = []
+    ab_dtype = problems[0].segs[0][0].dtype
+    dev = problems[0].out.device
+    need = 1
+    for i, pr in enumerate(problems):
+        ns = len(pr.segs)
+        if ns > L.GROUPED_MAX_SEGMENTS:
+            raise RuntimeError("unsloth_b200.gemm_grouped: at most %d segments per problem" % L.GROUPED_MAX_SEGMENTS)
+        sa = (L.GemmSegment * ns)()
+        for j, sg in enumerate(pr.segs):
+            A, B, K = sg[0], sg[1], sg[2]
+            _check_operand(A); _check_operand(B)
+            if A.dtype != ab_dtype or B.dtype != ab_dtype:
+                raise RuntimeError("unsloth_b200.gemm_grouped: mixed operand dtypes %s/%s" % (A.dtype, B.dtype))
+            sa[j].a = A.data_ptr(); sa[j].lda = A.stride(0)
+            sa[j].b = B.data_ptr(); sa[j].ldb = B.stride(0)
+            sa[j].k = K
+        keep.append(sa)
+        g = arr[i]
+        g.M, g.N, g.segs, g.n_segs = pr.M, pr.N, sa, ns
+        g.a_mn_major, g.b_mn_major = int(pr.a_mn), int(pr.b_mn)
+        g.C, g.ldc, g.c_dtype = pr.out.data_ptr(), pr.out.stride(0), L.dt(pr.out)
+        g.alpha, g.accumulate = float(pr.alpha), int(pr.accumulate)
+        kb = sum((sg[2] + 63) // 64 for sg in pr.segs)
+        split = max(1, min(int(pr.split_k), kb))
+        g.split_k = split
+        if split > 1:
+            ws = torch.empty(split * pr.M * pr.N, dtype=torch.float32, device=dev)
+            keep.append(ws)
+            g.workspace = ws.data_ptr()
+        g.block_n, g.signals = pr.block_n, int(pr.signals)
+        if pr.wait is None:
+            g.wait_problem, g.wait_segment, g.wait_all = -1, 0, 0
+        else:
+            g.wait_problem, g.wait_segment, g.wait_all = int(pr.wait[0]), int(pr.wait[1]), int(bool(pr.wait[2]))
+        m_pairs = (pr.M + 255) // 256
+        need += m_pairs + 1 + (m_pairs * ((pr.N + pr.block_n - 1) // pr.block_n) * 8 if split > 1 else 0)
+    if need > _GROUP_SCRATCH_INTS:
+        raise RuntimeError("unsloth_b200.gemm_grouped: scratch too small (%d ints needed)" % need)
+    scratch = _group_scratch(dev)
+    ev = GEMM_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("ub200_gemm_grouped", arr, n, L.dt(ab_dtype), L.ptr(scratch), L.stream())
+    if ev is not None:
+        e1.record()
+        ev.append((sum(pr.flops() for pr in problems), e0, e1,
+                   {"kernel": "grouped", "dense_flops": sum(pr.flops() for pr in problems if pr.tag == "dense"),
+                    "rank_flops": sum(pr.flops() for pr in problems if pr.tag != "dense"), "problems": n}))
+    return [pr.out for pr in problems]
 
 
 def cast_pad(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
