@@ -246,6 +246,37 @@ int ub200_gemm_grouped(const ub200_gemm_problem* probs, int n_probs, int ab_dtyp
                        cudaStream_t stream);
 int ub200_gemm_grouped_scratch_ints(const ub200_gemm_problem* probs, int n_probs, int* ints);
 
+/* ---- causal attention (tcgen05 / TMEM / TMA) ---------------------------------------------------
+ * The attention product between fast_rope_embedding and apply_o, which the reference delegates to
+ * flash-attn / xformers / SDPA (unsloth/utils/attention_dispatch.py:298-617; sliding window
+ * models/mistral.py:112-157; soft-capping + window models/gemma2.py:139-199).
+ * Q [tokens, Hq*D], K / V [tokens, Hk*D]: rows of the projection buffers (row strides in elements,
+ * head h at column h*D; tokens = batch*seqlen), O [tokens, Hq*D], lse fp32 [batch, Hq, seqlen]
+ * (varlen: [Hq, tokens]) = natural-log row sums, needed by the backward (may be NULL).
+ * Causal always.  window_left >= 0: key j visible to query i iff i - window_left <= j <= i (the
+ * reference's flash-attn window_size=(w, w) under causal masking); < 0: unlimited.  softcap > 0:
+ * scores = softcap * tanh(scale * qk / softcap).  cu_seqlens != NULL (int32 [n_docs+1], device):
+ * packed rows, batch must be 1, attention is block-diagonal per document.  D in {64, 128, 256}.  */
+int ub200_attention_fwd(const void* Q, const void* K, const void* V, void* O, float* lse,
+                        const int32_t* cu_seqlens, int n_docs, int max_seqlen, int batch, int seqlen,
+                        int n_heads_q, int n_heads_k, int head_dim, int64_t q_row_stride,
+                        int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                        float softmax_scale, int window_left, float softcap, int dtype,
+                        cudaStream_t stream);
+
+/* Backward of ub200_attention_fwd: dQ [tokens, Hq*D], dK / dV [tokens, Hk*D] (contiguous) from dO, the
+ * forward's O (contiguous [tokens, Hq*D]) and lse.  `delta` is caller-provided fp32 scratch shaped
+ * like lse.  P is recomputed; dK/dV are accumulated per key tile over all query heads of the group
+ * and dQ per query tile, both in TMEM -- no atomics, run-to-run bit-identical.  D in {64, 128}
+ * (D = 256 would need 768 TMEM columns: UB200_ERR_UNSUPPORTED).                                    */
+int ub200_attention_bwd(const void* dO, const void* Q, const void* K, const void* V, const void* O,
+                        const float* lse, float* delta, void* dQ, void* dK, void* dV,
+                        const int32_t* cu_seqlens, int n_docs, int max_seqlen, int batch, int seqlen,
+                        int n_heads_q, int n_heads_k, int head_dim, int64_t q_row_stride,
+                        int64_t k_row_stride, int64_t v_row_stride, int64_t do_row_stride,
+                        float softmax_scale, int window_left, float softcap, int dtype,
+                        cudaStream_t stream);
+
 /* ---- small helpers of the LoRA path ---------------------------------------------------------
  * Writes the whole [dst_rows, dst_cols] destination: the block at (dst_row_off, dst_col_off)
  * receives scale * src (src is [rows, cols]; transposed first when transpose != 0, i.e. the

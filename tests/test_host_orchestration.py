@@ -43,9 +43,12 @@ def gemm_grouped_double(problems):
     for i, pr in enumerate(problems):
         if pr.wait is not None:
             dep, seg, whole = pr.wait
-            assert 0 <= dep < i and problems[dep].signals and 0 <= seg < len(pr.segs)
-            operand = pr.segs[seg][1] if whole else pr.segs[seg][0]
-            assert operand.data_ptr() == problems[dep].out.data_ptr()
+            if not isinstance(dep, int):                     # producer given by identity
+                dep = next((k for k, q in enumerate(problems) if q is dep), None)
+            if dep is not None:                              # None: produced by an EARLIER launch
+                assert 0 <= dep < i and problems[dep].signals and 0 <= seg < len(pr.segs)
+                operand = pr.segs[seg][1] if whole else pr.segs[seg][0]
+                assert operand.data_ptr() == problems[dep].out.data_ptr()
         assert not (pr.b_mn and pr.block_n < 128)
         gemm_double(pr.M, pr.N, pr.segs, pr.out, pr.a_mn, pr.b_mn, pr.alpha, pr.accumulate)
     return [pr.out for pr in problems]
@@ -58,10 +61,11 @@ def cast_pad_double(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
     return dst
 
 
-@pytest.fixture(params=["grouped", "per-gemm"])
+@pytest.fixture(params=["rank-group+dense", "one-launch", "per-gemm"])
 def host_doubles(monkeypatch, request):
     import unsloth_b200._lib as L
-    monkeypatch.setenv("UB200_GROUPED", "1" if request.param == "grouped" else "0")
+    monkeypatch.setenv("UB200_GROUPED", "0" if request.param == "per-gemm" else "1")
+    monkeypatch.setenv("UB200_GROUPED_BWD", "1" if request.param == "one-launch" else "2")
     import unsloth_b200.kernels.fast_lora as FL
     import unsloth_b200.kernels.utils as KU
     monkeypatch.setattr(L, "require_cuda", lambda *a, **k: None)

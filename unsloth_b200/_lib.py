@@ -86,6 +86,9 @@ _SIGS = {
     "ub200_gemm_workspace_bytes": ([_i, _i, _i, POINTER(c_int64)], c_int),
     "ub200_gemm_grouped": ([POINTER(GemmProblem), _i, _i, _p, _p], c_int),
     "ub200_gemm_grouped_scratch_ints": ([POINTER(GemmProblem), _i, POINTER(c_int)], c_int),
+    "ub200_attention_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _l, _f, _i, _f, _i, _p], c_int),
+    "ub200_attention_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _l,
+                             _f, _i, _f, _i, _p], c_int),
     "ub200_cast_pad_2d": ([_p, _i, _l, _i, _i, _p, _i, _l, _i, _i, _i, _i, _f, _i, _p], c_int),
     "ub200_adamw_flat": ([_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _f, _p], c_int),
 }

@@ -138,7 +138,9 @@ __device__ __forceinline__ void store_row32(const Out& o, float (&v)[32], int ro
         *reinterpret_cast<float4*>(cptr + i) = t;
       }
     } else {
-      for (int i = 0; i < 32 && col0 + i < o.N; ++i) cptr[i] = o.accumulate ? cptr[i] + v[i] : v[i];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)          // fully unrolled: v[] stays in registers
+        if (col0 + i < o.N) cptr[i] = o.accumulate ? cptr[i] + v[i] : v[i];
     }
   } else {
     uint16_t* cptr = reinterpret_cast<uint16_t*>(o.C) + (int64_t)row * o.ldc + col0;
@@ -168,11 +170,14 @@ __device__ __forceinline__ void store_row32(const Out& o, float (&v)[32], int ro
         *reinterpret_cast<uint4*>(cptr + i) = q;
       }
     } else {
-      for (int i = 0; i < 32 && col0 + i < o.N; ++i) {
-        float val = v[i];
-        if (o.accumulate)
-          val += bf ? __bfloat162float(__ushort_as_bfloat16(cptr[i])) : __half2float(__ushort_as_half(cptr[i]));
-        cptr[i] = bf ? __bfloat16_as_ushort(__float2bfloat16_rn(val)) : __half_as_ushort(__float2half_rn(val));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col0 + i < o.N) {
+          float val = v[i];
+          if (o.accumulate)
+            val += bf ? __bfloat162float(__ushort_as_bfloat16(cptr[i])) : __half2float(__ushort_as_half(cptr[i]));
+          cptr[i] = bf ? __bfloat16_as_ushort(__float2bfloat16_rn(val)) : __half_as_ushort(__float2half_rn(val));
+        }
       }
     }
   }
@@ -251,10 +256,20 @@ gemm_grouped_kernel(const __grid_constant__ Params p) {
       const int n0 = n_blk * q.block_n + (int)rank * half_n;
       const uint32_t stage_tx = A_BYTES + (uint32_t)half_n * BLOCK_K * 2;
       bool waited = q.wait_prob < 0;
-      int seg = 0, seg_start = 0;
+      const int a_mn = q.a_mn, b_mn = q.b_mn, wait_seg = q.wait_seg;
+      // segment boundaries in registers: the k loop must not chase the parameter bank
+      int seg_end[MAX_SEGS];
+      {
+        int acc_kb = 0;
+#pragma unroll
+        for (int s = 0; s < MAX_SEGS; ++s) { acc_kb += (s < q.n_segs) ? q.seg_kblocks[s] : 0; seg_end[s] = acc_kb; }
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
-        while (kb >= seg_start + q.seg_kblocks[seg]) { seg_start += q.seg_kblocks[seg]; ++seg; }
-        if (!waited && seg >= q.wait_seg) {
+        int seg = 0, seg_start = 0;
+#pragma unroll
+        for (int s = 0; s < MAX_SEGS - 1; ++s)
+          if (kb >= seg_end[s]) { seg = s + 1; seg_start = seg_end[s]; }
+        if (!waited && seg >= wait_seg) {
           // the operand of this segment is produced by an earlier problem of THIS launch
           const Prob& d = p.probs[q.wait_prob];
           const int* flag = p.scratch + d.flag_base + (q.wait_all ? d.m_pairs : m_pair);
@@ -271,14 +286,14 @@ gemm_grouped_kernel(const __grid_constant__ Params p) {
         if (elect_one()) {
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_tx);
           else mbar_arrive_remote(full_bar(stage), 0u);
-          if (!q.a_mn) {
+          if (!a_mn) {
             tma_load_2d_2sm(sa, &q.tmap_a[seg], full_bar(stage), k0, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)
               tma_load_2d_2sm(sa + j * 8192u, &q.tmap_a[seg], full_bar(stage), m0 + j * 64, k0);
           }
-          if (!q.b_mn) {
+          if (!b_mn) {
             tma_load_2d_2sm(sb, &q.tmap_b[seg], full_bar(stage), k0, n0);
           } else {
             for (int j = 0; j < half_n / 64; ++j)
@@ -407,7 +422,9 @@ gemm_grouped_kernel(const __grid_constant__ Params p) {
                     v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
                   }
                 } else {
-                  for (int i = 0; i < ncol; ++i) v[i] += __ldcg(src + i);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (i < ncol) v[i] += __ldcg(src + i);
                 }
               }
               store_row32(f, v, row, col0);

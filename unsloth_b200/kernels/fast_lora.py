@@ -36,6 +36,36 @@ def _grouped():
     return os.environ.get("UB200_GROUPED", "1") != "0"
 
 
+def _fwd_grouped():
+    """Forward: XA = X @ A_cat^T produced inside the launch of the projections that consume it."""
+    return _grouped() and os.environ.get("UB200_GROUPED_FWD", "1") != "0"
+
+
+def _bwd_mode():
+    """Backward schedule of a projection group:
+      0  one launch per GEMM (round 1);
+      1  everything in one persistent launch (rank-block tiles share the SMs with the dense tiles);
+      2  TWO launches: all rank-block products of the phase (G, dB_i, dA -- HBM-bound streams) as one
+         grouped launch that fills the machine, then the dense dX GEMM alone, so that the streaming
+         tiles do not evict the dense GEMM's L2-resident operand (measured: profiles/r2_lora_group_bench.log)."""
+    if not _grouped():
+        return 0
+    return int(os.environ.get("UB200_GROUPED_BWD", "2"))
+
+
+def _launch_backward(front, dense, tail):
+    """front: rank-block producers / dB reductions; dense: the dX (or DW) GEMM; tail: dA (needs all of G)."""
+    if _bwd_mode() == 1:
+        probs = front + dense + tail
+        if probs:
+            gemm_grouped(probs)
+        return
+    if front or tail:
+        gemm_grouped(front + tail)
+    if dense:
+        gemm_grouped(dense)
+
+
 def _split_k_grouped(T):
     """Split factor of the token reductions (dA / dB) inside a grouped launch: ~32 k-blocks (2048
     tokens) per work item, so the items are short enough to fill the tail of the launch."""
@@ -122,7 +152,7 @@ class _Group:
     def forward(self, keep=False):
         """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None.  `keep`: the
         dequantised weights are private tensors left in `self.dense` for the backward."""
-        if _grouped():
+        if _fwd_grouped():
             return self._forward_grouped(keep)
         X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
         if keep:
@@ -187,18 +217,17 @@ class _Group:
         gemm_grouped(probs)
         return outs, XA
 
-    def backward_problems(self, dYs, XA, dX_out=None, need_dX=True, extra_front=(), extra_mid=()):
-        """The problems of this group's backward as ONE list (producer G first):
-            G = sum_i dY_i @ (s_i B_i)            [T, Rp]   rank block, signals
-            dB_i = s_i dY_i^T @ XA                [out_i, Rp] fp32, split-K over tokens
-            (extra_mid: problems of a neighbouring group that ride in the same launch)
-            dX = sum_i dY_i @ W_i + G @ A_cat     waits for its row block of G
-            dA_cat^T = X^T @ G                    [in, Rp] fp32, split-K, waits for all of G
-        Returns (problems, finish) where finish() -> (dX or None, [(dA_i, dB_i)...])."""
+    def backward_problems(self, dYs, XA, dX_out=None, need_dX=True, extra_front=()):
+        """The problems of this group's backward:
+          front  G = sum_i dY_i @ (s_i B_i)          [T, Rp]   rank block (signals)
+                 dB_i = s_i dY_i^T @ XA              [out_i, Rp] fp32, split-K over tokens
+                 (+ extra_front: rank-block problems of a neighbouring group riding along)
+          dense  dX = sum_i dY_i @ W_i + G @ A_cat   waits for its row block of G (same launch only)
+          tail   dA_cat^T = X^T @ G                  [in, Rp] fp32, split-K, waits for all of G
+        Returns (front, dense, tail, finish) with finish() -> (dX or None, [(dA_i, dB_i)...])."""
         X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
-        probs = list(extra_front)
-        g_idx = None
-        G = dA_catT = None
+        front, dense, tail = list(extra_front), [], []
+        G = dA_catT = pG = None
         dB_fulls = []
         sk = _split_k_grouped(T)
         if self.has_lora:
@@ -211,19 +240,17 @@ class _Group:
                 B_pad = cached_cast_pad(Bc, (out_f, Rp), dt, col_off=off, scale=s)
                 segs.append((dY, B_pad, out_f))
             G = torch.empty((T, Rp), dtype=dt, device=dev)
-            g_idx = len(probs)
-            # several segments of G may exceed the per-problem limit only with > 4 adapters per group
-            probs.append(Problem(T, Rp, segs, G, b_mn=True, signals=True, tag="rank"))
+            pG = Problem(T, Rp, segs, G, b_mn=True, signals=True, tag="rank")
+            front.insert(0, pG)
             for dY, (W, Wq, A, B, s) in zip(dYs, self.projs):
                 if A is None:
                     dB_fulls.append(None)
                     continue
                 out_f = dY.shape[1]
                 dB_full = torch.empty((out_f, Rp), dtype=torch.float32, device=dev)
-                probs.append(Problem(out_f, Rp, [(dY, XA, T)], dB_full, a_mn=True, b_mn=True, alpha=s,
+                front.append(Problem(out_f, Rp, [(dY, XA, T)], dB_full, a_mn=True, b_mn=True, alpha=s,
                                      split_k=sk, tag="rank"))
                 dB_fulls.append(dB_full)
-        probs.extend(extra_mid)
         dX = None
         if need_dX:
             segs = []
@@ -237,17 +264,17 @@ class _Group:
             wait = None
             if self.has_lora:
                 segs.append((G, self.A_cat(), Rp, self.rank_total))
-                wait = (g_idx, len(segs) - 1, False)
-            # dA = X^T @ G reads X in the SAME launch, so dX cannot be written over the saved X buffer
-            # (the reference's inplace=True is a memory optimisation, fast_lora.py:194, 498; the
-            # 67 MB it saves is transient here)
+                wait = (pG, len(segs) - 1, False)
+            # dA = X^T @ G may read X while dX tiles are being stored: dX is never written over the
+            # saved X buffer when adapters are active (the reference's inplace=True is a memory
+            # optimisation, fast_lora.py:194, 498; the 67 MB it saves is transient here)
             inplace_ok = dX_out is not None and not self.has_lora
             dX = dX_out if inplace_ok else torch.empty((T, self.in_f), dtype=dt, device=dev)
-            probs.append(Problem(T, self.in_f, segs, dX, b_mn=True, wait=wait))
+            dense.append(Problem(T, self.in_f, segs, dX, b_mn=True, wait=wait))
         if self.has_lora:
             dA_catT = torch.empty((self.in_f, Rp), dtype=torch.float32, device=dev)
-            probs.append(Problem(self.in_f, Rp, [(X2, G, T)], dA_catT, a_mn=True, b_mn=True, split_k=sk,
-                                 wait=(g_idx, 0, True), tag="rank"))
+            tail.append(Problem(self.in_f, Rp, [(X2, G, T)], dA_catT, a_mn=True, b_mn=True, split_k=sk,
+                                wait=(pG, 0, True), tag="rank"))
 
         def finish():
             grads = []
@@ -258,14 +285,13 @@ class _Group:
                 r = A.shape[0]
                 grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
             return dX, grads
-        return probs, finish
+        return front, dense, tail, finish
 
     def backward(self, dYs, XA, dX_out=None, need_dX=True):
         """dYs: list of [T, out_i].  Returns (dX [T,in] or None, [(dA_i, dB_i) or (None, None)])."""
-        if _grouped():
-            probs, finish = self.backward_problems(dYs, XA, dX_out, need_dX)
-            if probs:
-                gemm_grouped(probs)
+        if _bwd_mode():
+            front, dense, tail, finish = self.backward_problems(dYs, XA, dX_out, need_dX)
+            _launch_backward(front, dense, tail)
             return finish()
         X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
         grads = []
@@ -373,7 +399,7 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
         dY2 = _as2d(dY)
         T = X2.shape[0]
         dt, dev = X2.dtype, X2.device
-        if _grouped():
+        if _bwd_mode():
             return LoRA_MLP._backward_grouped(ctx, dY2, X2, e, g, XA1, XA2)
         # --- down projection: DW = dY @ W_down + (dY @ s B_down) @ A_down          (:155)
         # `h` is not needed yet: a group over a placeholder input gives DW and G_down
@@ -444,22 +470,20 @@ def _mlp_backward_grouped(ctx, dY2, X2, e, g, XA1, XA2):
     if not b_mn:
         Bop, b_mn = Bop.t().contiguous(), True
     sk = _split_k_grouped(T)
-    probs, G_down, dB_full = [], None, None
+    front, G_down, dB_full, pG = [], None, None, None
     segs, wait = [(dY2, Bop, Hout)], None
     if downA is not None:
         Bc = downB if downB.stride(-1) == 1 else downB.contiguous()
         B_pad = cached_cast_pad(Bc, (Bc.shape[0], down.Rp), dt, scale=downS)     # as in forward
         G_down = torch.empty((T, down.Rp), dtype=dt, device=dev)
-        probs.append(Problem(T, down.Rp, [(dY2, B_pad, Bc.shape[0])], G_down, b_mn=True, signals=True, tag="rank"))
-        segs.append((G_down, down.A_cat(), down.Rp, downA.shape[0]))
-        wait = (0, 1, False)
-    DW = torch.empty((T, I), dtype=dt, device=dev)
-    probs.append(Problem(T, I, segs, DW, b_mn=True, wait=wait))
-    if downA is not None:
+        pG = Problem(T, down.Rp, [(dY2, B_pad, Bc.shape[0])], G_down, b_mn=True, signals=True, tag="rank")
         dB_full = torch.empty((Hout, down.Rp), dtype=torch.float32, device=dev)
-        probs.append(Problem(Hout, down.Rp, [(dY2, XA2, T)], dB_full, a_mn=True, b_mn=True, alpha=downS,
-                             split_k=sk, tag="rank"))
-    gemm_grouped(probs)
+        front = [pG, Problem(Hout, down.Rp, [(dY2, XA2, T)], dB_full, a_mn=True, b_mn=True, alpha=downS,
+                             split_k=sk, tag="rank")]
+        segs.append((G_down, down.A_cat(), down.Rp, downA.shape[0]))
+        wait = (pG, 1, False)
+    DW = torch.empty((T, I), dtype=dt, device=dev)
+    _launch_backward(front, [Problem(T, I, segs, DW, b_mn=True, wait=wait)], [])
     h, df, de = _backward_function(DW, e, g)                       # in place            (:156-157)
     extra, dA_T = [], None
     if downA is not None:
@@ -467,8 +491,9 @@ def _mlp_backward_grouped(ctx, dY2, X2, e, g, XA1, XA2):
         extra = [Problem(I, down.Rp, [(h, G_down, T)], dA_T, a_mn=True, b_mn=True, split_k=sk, tag="rank")]
     grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
     grp.dense = dense_gu
-    probs, finish = grp.backward_problems([de, df], XA1, dX_out=X2 if ctx.inplace else None, extra_mid=extra)
-    gemm_grouped(probs)
+    front, dense, tail, finish = grp.backward_problems([de, df], XA1, dX_out=X2 if ctx.inplace else None,
+                                                       extra_front=extra)
+    _launch_backward(front, dense, tail)
     dX, ((d_gateA, d_gateB), (d_upA, d_upB)) = finish()
     d_downA = d_downB = None
     if downA is not None:

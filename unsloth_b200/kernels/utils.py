@@ -227,8 +227,8 @@ class Problem:
     """One problem of a grouped launch: out[M,N] (+)= alpha * sum_s A_s . B_s^T.
     segs: (A, B, K) or (A, B, K, K_true) -- K_true is the algorithmic reduction length (the LoRA
     rank for a zero-padded rank block), used only for flop accounting.
-    wait: None or (index of an earlier problem whose output this one reads, first segment that
-    reads it, whole_output: bool)."""
+    wait: None or (earlier problem whose output this one reads -- its index in the launch list or the
+    Problem object itself --, first segment that reads it, whole_output: bool)."""
     __slots__ = ("M", "N", "segs", "out", "a_mn", "b_mn", "alpha", "accumulate", "split_k", "block_n",
                  "signals", "wait", "tag")
 
@@ -296,10 +296,16 @@ def gemm_grouped(problems):
             keep.append(ws)
             g.workspace = ws.data_ptr()
         g.block_n, g.signals = pr.block_n, int(pr.signals)
-        if pr.wait is None:
+        dep = pr.wait
+        if dep is not None and isinstance(dep[0], Problem):
+            # producer given by identity: a producer that is NOT part of this launch has already
+            # completed in an earlier launch on the stream -- nothing to wait for
+            idx = next((k for k, q_ in enumerate(problems) if q_ is dep[0]), -1)
+            dep = None if idx < 0 else (idx, dep[1], dep[2])
+        if dep is None:
             g.wait_problem, g.wait_segment, g.wait_all = -1, 0, 0
         else:
-            g.wait_problem, g.wait_segment, g.wait_all = int(pr.wait[0]), int(pr.wait[1]), int(bool(pr.wait[2]))
+            g.wait_problem, g.wait_segment, g.wait_all = int(dep[0]), int(dep[1]), int(bool(dep[2]))
         m_pairs = (pr.M + 255) // 256
         need += m_pairs + 1 + (m_pairs * ((pr.N + pr.block_n - 1) // pr.block_n) * 8 if split > 1 else 0)
     if need > _GROUP_SCRATCH_INTS:
