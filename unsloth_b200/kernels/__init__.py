@@ -13,3 +13,4 @@ from .fast_lora import (get_lora_parameters, get_lora_parameters_bias, apply_lor
                         apply_lora_o, LoRA_MLP, LoRA_QKV, LoRA_W)
 from .utils import (fast_dequantize, matmul_lora, QUANT_STATE, gemm, fast_gemv,
                     fast_linear_forward)
+from .attention import fast_attention, Fast_Attention, attention_forward, attention_backward

@@ -36,26 +36,38 @@ def _grouped():
     return os.environ.get("UB200_GROUPED", "1") != "0"
 
 
-def _fwd_grouped():
+# Launch schedule per phase.  "auto" = what the interleaved A/B at cfg2 sizes measured as fastest
+# (benchmarks/lora_group_bench.py, profiles/r2_lora_group_bench.log): the rank-block products are
+# HBM-bound streams that already run at 0.65-1.0 of the copy bandwidth as separate launches, so
+# grouping only removes launch gaps and fill/drain -- worth it where the streams are short (q/k/v/o
+# backward: -8 %, MLP forward: -1 %), not where they are long (MLP backward: +4-6 % because the
+# streaming tiles evict the dense GEMM's L2-resident operand).
+_AUTO_FWD = {"qkv": False, "o": True, "mlp": True}
+_AUTO_BWD = {"qkv": 1, "o": 1, "mlp": 0}
+
+
+def _fwd_grouped(kind="mlp"):
     """Forward: XA = X @ A_cat^T produced inside the launch of the projections that consume it."""
-    return _grouped() and os.environ.get("UB200_GROUPED_FWD", "1") != "0"
+    if not _grouped():
+        return False
+    v = os.environ.get("UB200_GROUPED_FWD", "auto")
+    return _AUTO_FWD.get(kind, True) if v == "auto" else v != "0"
 
 
-def _bwd_mode():
+def _bwd_mode(kind="mlp"):
     """Backward schedule of a projection group:
       0  one launch per GEMM (round 1);
       1  everything in one persistent launch (rank-block tiles share the SMs with the dense tiles);
-      2  TWO launches: all rank-block products of the phase (G, dB_i, dA -- HBM-bound streams) as one
-         grouped launch that fills the machine, then the dense dX GEMM alone, so that the streaming
-         tiles do not evict the dense GEMM's L2-resident operand (measured: profiles/r2_lora_group_bench.log)."""
+      2  TWO launches: all rank-block products of the phase (G, dB_i, dA) grouped, then the dense dX."""
     if not _grouped():
         return 0
-    return int(os.environ.get("UB200_GROUPED_BWD", "2"))
+    v = os.environ.get("UB200_GROUPED_BWD", "auto")
+    return _AUTO_BWD.get(kind, 0) if v == "auto" else int(v)
 
 
-def _launch_backward(front, dense, tail):
+def _launch_backward(front, dense, tail, mode):
     """front: rank-block producers / dB reductions; dense: the dX (or DW) GEMM; tail: dA (needs all of G)."""
-    if _bwd_mode() == 1:
+    if mode == 1:
         probs = front + dense + tail
         if probs:
             gemm_grouped(probs)
@@ -94,9 +106,10 @@ def _split_k(M, N, K):
 class _Group:
     """Projections (W, W_quant, A, B, s) that share one 2-D input X2 [T, in]."""
 
-    def __init__(self, X2, projs):
+    def __init__(self, X2, projs, kind="mlp"):
         self.X2 = X2
         self.projs = projs
+        self.kind = kind
         self.T, self.in_f = X2.shape
         self.dtype = X2.dtype
         self.dev = X2.device
@@ -152,7 +165,7 @@ class _Group:
     def forward(self, keep=False):
         """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None.  `keep`: the
         dequantised weights are private tensors left in `self.dense` for the backward."""
-        if _fwd_grouped():
+        if _fwd_grouped(self.kind):
             return self._forward_grouped(keep)
         X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
         if keep:
@@ -289,9 +302,10 @@ class _Group:
 
     def backward(self, dYs, XA, dX_out=None, need_dX=True):
         """dYs: list of [T, out_i].  Returns (dX [T,in] or None, [(dA_i, dB_i) or (None, None)])."""
-        if _bwd_mode():
+        mode = _bwd_mode(self.kind)
+        if mode:
             front, dense, tail, finish = self.backward_problems(dYs, XA, dX_out, need_dX)
-            _launch_backward(front, dense, tail)
+            _launch_backward(front, dense, tail, mode)
             return finish()
         X2, T, dt, dev, Rp = self.X2, self.T, self.dtype, self.dev, self.Rp
         grads = []
@@ -399,7 +413,7 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
         dY2 = _as2d(dY)
         T = X2.shape[0]
         dt, dev = X2.dtype, X2.device
-        if _bwd_mode():
+        if _bwd_mode("mlp"):
             return LoRA_MLP._backward_grouped(ctx, dY2, X2, e, g, XA1, XA2)
         # --- down projection: DW = dY @ W_down + (dY @ s B_down) @ A_down          (:155)
         # `h` is not needed yet: a group over a placeholder input gives DW and G_down
@@ -483,7 +497,8 @@ def _mlp_backward_grouped(ctx, dY2, X2, e, g, XA1, XA2):
         segs.append((G_down, down.A_cat(), down.Rp, downA.shape[0]))
         wait = (pG, 1, False)
     DW = torch.empty((T, I), dtype=dt, device=dev)
-    _launch_backward(front, [Problem(T, I, segs, DW, b_mn=True, wait=wait)], [])
+    mode = _bwd_mode("mlp")
+    _launch_backward(front, [Problem(T, I, segs, DW, b_mn=True, wait=wait)], [], mode)
     h, df, de = _backward_function(DW, e, g)                       # in place            (:156-157)
     extra, dA_T = [], None
     if downA is not None:
@@ -493,7 +508,7 @@ def _mlp_backward_grouped(ctx, dY2, X2, e, g, XA1, XA2):
     grp.dense = dense_gu
     front, dense, tail, finish = grp.backward_problems([de, df], XA1, dX_out=X2 if ctx.inplace else None,
                                                        extra_front=extra)
-    _launch_backward(front, dense, tail)
+    _launch_backward(front, dense, tail, mode)
     dX, ((d_gateA, d_gateB), (d_upA, d_upB)) = finish()
     d_downA = d_downB = None
     if downA is not None:
@@ -547,7 +562,7 @@ class LoRA_QKV(GradModeAware, torch.autograd.Function):
         shape = X.shape
         X2 = _as2d(X)
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
-                          (VW, VW_quant, VA, VB, VS)])
+                          (VW, VW_quant, VA, VB, VS)], kind="qkv")
         (Q, K, V), XA = grp.forward(keep_for_backward(ctx.needs_input_grad))
         ctx.dense = grp.dense
         if len(shape) == 3:
@@ -566,7 +581,7 @@ class LoRA_QKV(GradModeAware, torch.autograd.Function):
         QA, QB, KA, KB, VA, VB = ctx.lora
         X2, XA = ctx.saved_tensors
         grp = _Group(X2, [(QW, QW_quant, QA, QB, QS), (KW, KW_quant, KA, KB, KS),
-                          (VW, VW_quant, VA, VB, VS)])
+                          (VW, VW_quant, VA, VB, VS)], kind="qkv")
         grp.dense, ctx.dense = ctx.dense, None
         need_dX = ctx.needs_input_grad[0]     # False for the first layer (embedding output)
         dX, ((dQA, dQB), (dKA, dKB), (dVA, dVB)) = grp.backward(
@@ -593,7 +608,7 @@ class LoRA_W(GradModeAware, torch.autograd.Function):
         L.require_cuda(X)
         shape = X.shape
         X2 = _as2d(X)
-        grp = _Group(X2, [(W, W_quant, A, B, S)])
+        grp = _Group(X2, [(W, W_quant, A, B, S)], kind="o")
         (XW,), XA = grp.forward(keep_for_backward(ctx.needs_input_grad))
         ctx.dense = grp.dense
         ctx.custom_saved_tensors = (W, W_quant, S)
@@ -608,7 +623,7 @@ class LoRA_W(GradModeAware, torch.autograd.Function):
         W, W_quant, S = ctx.custom_saved_tensors
         A, B = ctx.lora
         X2, XA = ctx.saved_tensors
-        grp = _Group(X2, [(W, W_quant, A, B, S)])
+        grp = _Group(X2, [(W, W_quant, A, B, S)], kind="o")
         grp.dense, ctx.dense = ctx.dense, None
         dX, ((dA, dB),) = grp.backward([_as2d(dY)], XA)
         return dX.view(ctx.shape), None, None, dA, dB, None

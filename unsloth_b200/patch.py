@@ -89,14 +89,25 @@ class RotaryCache:
 _SDPA_CUDNN = {"ok": None}
 
 
+def _attention_policy():
+    """UB200_ATTENTION = own | auto | library.
+      own      every attention product runs on csrc/attention.cu (tcgen05 / TMEM / TMA);
+      auto     (default) csrc/attention.cu wherever the reference's dispatcher would have called
+               flash-attn 2 -- sliding window, soft-capping, packed rows, head_dim 256 (1.4-2.3x faster
+               than flash-attn 2 on a B200, benchmarks/attn_bench.py) -- and cuDNN's fused attention
+               through torch SDPA for plain dense causal attention, where cuDNN is still ahead;
+      library  round-1 behaviour (cuDNN SDPA / flash-attn 2 only)."""
+    return os.environ.get("UB200_ATTENTION", "auto")
+
+
 def _attention(Q, K_, V, scale, window, softcap, seq_info=None):
-    """External library call, like the reference's dispatcher (utils/attention_dispatch.py:298-617:
-    flash-attn | xformers | SDPA), on [B, S, H, D] views of the projection buffers (GQA native,
-    no copies).  Plain causal attention goes to torch SDPA's cuDNN backend (Blackwell-native fused
-    attention, ~3x flash-attn 2 on B200, benchmarks/attn_bench.py); sliding window / soft-capping
-    (Mistral, Gemma-2) go to flash-attn 2, which supports them.  Packed rows (`seq_info` =
-    (lengths, cu_seqlens, max_seqlen), packing.py:586-606) take flash-attn's varlen entry with the
-    reference's arguments (attention_dispatch.py:433-447): block-diagonal causal, no copies."""
+    """The attention product on [B, S, H, D] views of the projection buffers (GQA native, no copies);
+    the reference's dispatcher is utils/attention_dispatch.py:298-617 (flash-attn | xformers | SDPA;
+    packed rows :433-447)."""
+    policy = _attention_policy()
+    special = seq_info is not None or window != (-1, -1) or bool(softcap) or Q.shape[-1] == 256
+    if policy == "own" or (policy == "auto" and special):
+        return K.fast_attention(Q, K_, V, scale, window, softcap, seq_info)
     if seq_info is not None:
         from flash_attn import flash_attn_varlen_func
         bsz, q_len, n_heads, hd = Q.shape
@@ -119,7 +130,9 @@ def _attention(Q, K_, V, scale, window, softcap, seq_info=None):
         except RuntimeError:
             if _SDPA_CUDNN["ok"]:
                 raise
-            _SDPA_CUDNN["ok"] = False          # backend unavailable for this shape: use flash-attn
+            _SDPA_CUDNN["ok"] = False          # backend unavailable for this shape: use our kernel
+            if policy != "library":
+                return K.fast_attention(Q, K_, V, scale, window, softcap, seq_info)
     from flash_attn import flash_attn_func
     return flash_attn_func(Q, K_, V, dropout_p=0.0, softmax_scale=scale, causal=True,
                            window_size=window, softcap=softcap)
