@@ -57,8 +57,10 @@ def parse():
     ap.add_argument("--rank", type=int, default=RANK_R)
     ap.add_argument("--sliding-window", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--gradient-checkpointing", action="store_true",
-                    help="recompute every decoder layer in the backward (off: the BASELINE configs fit a B200)")
+    ap.add_argument("--gradient-checkpointing", nargs="?", const="true", default=None, choices=["true", "unsloth"],
+                    help="recompute every decoder layer in the backward; `unsloth` also parks the layer inputs in "
+                         "pinned host memory (off: the BASELINE configs fit a B200)")
+    ap.add_argument("--tiled-mlp", type=int, default=0, help="run the MLP over N token shards (recomputed shard-wise)")
     ap.add_argument("--no-keep-dequant", action="store_true",
                     help="re-dequantise the NF4 weights in the backward (the reference's schedule) instead of "
                          "keeping the forward's 16-bit expansion resident until the layer's backward")
@@ -259,7 +261,8 @@ def run_ours(args):
         KU.set_keep_dequant(False)
     model = build_qlora_model(args.model, r=args.rank, lora_alpha=args.rank, device=dev, seed=3407,
                               num_hidden_layers=args.layers,
-                              gradient_checkpointing=args.gradient_checkpointing, **extra)
+                              gradient_checkpointing={"true": True, "unsloth": "unsloth", None: False}[args.gradient_checkpointing],
+                              tiled_mlp=args.tiled_mlp, **extra)
     bucket = FlatLoRABucket(lora_parameters(model), lr=2e-4, weight_decay=0.01)
     bucket.broadcast_params(0)
     V = model.config.vocab_size
@@ -410,7 +413,7 @@ def run_ours(args):
                                     {"cfg3": 2, "cfg5": 4}.get(args.preset, 1 if world == 1 else 3),
                                     (" sliding_window=%d" % args.sliding_window) if args.sliding_window else ""),
                        "global_batch": args.bs * world, "seq_len": args.seq, "parallelism": "dp%d" % world,
-                       "layers": model.config.num_hidden_layers, "gradient_checkpointing": bool(args.gradient_checkpointing),
+                       "layers": model.config.num_hidden_layers, "gradient_checkpointing": args.gradient_checkpointing or False, "tiled_mlp": args.tiled_mlp,
                        "optimizer": "AdamW on the flat LoRA bucket (%d params)" % bucket.numel(),
                        "cuda_graph": graph_note,
                        "keep_dequant": ("dequantised weights stay resident from a layer's forward to its backward "

@@ -246,6 +246,18 @@ int ub200_gemm_grouped(const ub200_gemm_problem* probs, int n_probs, int ab_dtyp
                        cudaStream_t stream);
 int ub200_gemm_grouped_scratch_ints(const ub200_gemm_problem* probs, int n_probs, int* ints);
 
+/* ---- NF4 dequantisation fused into the tcgen05 GEMM's operand staging ---------------------------
+ * Y[M,N] = X[M,K] . dequant(W)[N,K]^T (+ lora_xa[M,lora_k] . lora_b[N,lora_k]^T): matmul_lora
+ * (unsloth/kernels/utils.py:1128-1170) without the 16-bit copy of W that fast_dequantize (:567-679)
+ * writes first.  W: bitsandbytes NF4 double-quant fields as in ub200_dequantize_nf4; blocksize 64 /
+ * 256 and K % 64 == 0 (one quantisation block per row and k-block).  lora_k: 0 or a multiple of 64
+ * (zero-padded rank block, lora_b already scaled).  Bit-identical to dequantise-then-ub200_gemm.  */
+int ub200_gemm_nf4(int M, int N, int K, const void* X, int64_t ldx, const uint8_t* packed,
+                   const uint8_t* absmax_q, const float* code2, const float* absmax2,
+                   const float* offset, int blocksize, int blocksize2, const void* lora_xa,
+                   int64_t ld_xa, const void* lora_b, int64_t ld_b, int lora_k, void* C, int64_t ldc,
+                   int dtype, cudaStream_t stream);
+
 /* ---- causal attention (tcgen05 / TMEM / TMA) ---------------------------------------------------
  * The attention product between fast_rope_embedding and apply_o, which the reference delegates to
  * flash-attn / xformers / SDPA (unsloth/utils/attention_dispatch.py:298-617; sliding window

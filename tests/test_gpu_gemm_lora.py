@@ -330,3 +330,26 @@ def test_fused_ce_odd_vocab_and_trainable_head():
     for n, a, b in (("dH", hg.grad, h32.grad), ("dW", Wg.grad, W32.grad), ("db", bg.grad, b32.grad)):
         e = (a.float() - b).abs().max().item()
         assert e < 3e-2 * b.abs().max().item() + 1e-7, (n, e)
+
+
+@pytest.mark.parametrize("T_,K,N,r", [(512, 512, 768, 16), (300, 1024, 200, 0), (8192, 4096, 14336, 16)])
+def test_fused_nf4_gemm_is_bit_identical_to_dequantise_then_gemm(T_, K, N, r):
+    """csrc/gemm_nf4.cu expands the NF4 weight inside the GEMM's operand staging; every weight is
+    rounded exactly as ub200_dequantize_nf4 rounds it and the k-blocks accumulate in the same order,
+    so the output must EQUAL dequantise -> ub200_gemm (with the LoRA rank block as the last segment)."""
+    from unsloth_b200.kernels.utils import fast_dequantize, gemm, gemm_nf4
+    from unsloth_b200.nf4 import quantize_nf4
+    torch.manual_seed(T_ + N)
+    X = (torch.randn(T_, K, device=DEV) * 0.5).to(BF)
+    W = (torch.randn(N, K, device=DEV) * 0.05).to(BF)
+    packed, qs = quantize_nf4(W)
+    Wd = fast_dequantize(packed, qs)
+    lora, segs = None, [(X, Wd, K)]
+    if r:
+        XA = torch.zeros(T_, 64, device=DEV, dtype=BF); XA[:, :r] = (torch.randn(T_, r, device=DEV) * 0.3).to(BF)
+        Bp = torch.zeros(N, 64, device=DEV, dtype=BF); Bp[:, :r] = (torch.randn(N, r, device=DEV) * 0.05).to(BF)
+        lora = (XA, Bp, 64)
+        segs.append((XA, Bp, 64))
+    ref = gemm(T_, N, segs, torch.empty(T_, N, device=DEV, dtype=BF), cta_group=2, block_n=256)
+    out = gemm_nf4(X, packed, qs, torch.empty(T_, N, device=DEV, dtype=BF), lora)
+    assert torch.equal(out, ref), (out.float() - ref.float()).abs().max().item()

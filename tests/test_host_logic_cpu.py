@@ -605,3 +605,51 @@ def test_no_grad_forward_does_not_keep_dequantised_weights(cpu_model):
             KU.fast_dequantize = orig
     finally:
         KU.set_keep_dequant(False)
+
+
+@pytest.mark.parametrize("name", ["llama-3-8b", "gemma-2-9b"])
+def test_offloaded_checkpoint_and_tiled_mlp_are_exact(cpu_model, name):
+    """`gradient_checkpointing="unsloth"` (layer inputs parked on the host, layer recomputed in the
+    backward) and `tiled_mlp=n` (MLP over token shards, recomputed shard-wise) change memory, not
+    arithmetic: same loss, same LoRA gradients as the plain step (fp32 through the ABI emulator)."""
+    P = cpu_model
+    extra = {"query_pre_attn_scalar": 16} if name == "gemma-2-9b" else {}
+    torch.manual_seed(3)
+    ids = torch.randint(0, TINY["vocab_size"], (2, 600))          # >= 512 tokens: offloading engages
+    labels = ids.clone(); labels[0, :7] = -100
+    base = _build(P, name, **extra)
+    out = base(input_ids=ids, labels=labels)
+    out.loss.backward()
+    g0 = _grads(P, base)
+    for kw in (dict(gradient_checkpointing="unsloth"), dict(tiled_mlp=3), dict(gradient_checkpointing=True, tiled_mlp=2)):
+        m = P.build_qlora_model(name, r=4, lora_alpha=8, device="cpu", dtype=torch.float32, num_hidden_layers=2,
+                                init_b_std=0.05, **dict(TINY, **extra), **kw)
+        o = m(input_ids=ids, labels=labels)
+        o.loss.backward()
+        assert abs(o.loss.item() - out.loss.item()) <= 1e-6 * abs(out.loss.item()), kw
+        torch.testing.assert_close(_grads(P, m), g0, rtol=1e-5, atol=1e-7)
+    from unsloth_b200.kernels import utils as KU
+    KU.KEEP_DEQUANT_BLOCKED = False
+
+
+@pytest.mark.parametrize("name,extra", [("llama-3-8b", {}), ("mistral-7b-v0.3", {"sliding_window": 6}),
+                                        ("gemma-2-9b", {"query_pre_attn_scalar": 16, "sliding_window": 6})])
+def test_kv_cache_decode_loop_matches_full_forward(cpu_model, name, extra):
+    """generate(): prefill + single-token KV-cache steps (llama.py:352-602) reproduce what the full
+    forward over the growing sequence predicts (greedy tokens identical, fp32 through the emulator)."""
+    from unsloth_b200.generate import generate
+    P = cpu_model
+    model = _build(P, name, **extra)
+    torch.manual_seed(5)
+    ids = torch.randint(0, TINY["vocab_size"], (1, 9))
+    out = generate(model, ids, max_new_tokens=6)
+    assert out.shape == (1, 15) and torch.equal(out[:, :9], ids)
+    cur = ids
+    with torch.no_grad():
+        for _ in range(6):
+            hidden = P.Model_fast_forward(model.model, cur)
+            logits = torch.nn.functional.linear(hidden[:, -1:], model.lm_head.weight).float()
+            if model._ub_final_softcap:
+                logits = model._ub_final_softcap * torch.tanh(logits / model._ub_final_softcap)
+            cur = torch.cat([cur, logits[:, -1].argmax(-1, keepdim=True)], 1)
+    assert torch.equal(out, cur)

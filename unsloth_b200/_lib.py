@@ -86,6 +86,7 @@ _SIGS = {
     "ub200_gemm_workspace_bytes": ([_i, _i, _i, POINTER(c_int64)], c_int),
     "ub200_gemm_grouped": ([POINTER(GemmProblem), _i, _i, _p, _p], c_int),
     "ub200_gemm_grouped_scratch_ints": ([POINTER(GemmProblem), _i, POINTER(c_int)], c_int),
+    "ub200_gemm_nf4": ([_i, _i, _i, _p, _l, _p, _p, _p, _p, _p, _i, _i, _p, _l, _p, _l, _i, _p, _l, _i, _p], c_int),
     "ub200_attention_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _l, _f, _i, _f, _i, _p], c_int),
     "ub200_attention_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _l,
                              _f, _i, _f, _i, _p], c_int),

@@ -305,8 +305,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
       asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
       mx = fmaxf(mx, xb[(ch ^ 1) * 128 + r]);
       const float m_new = fmaxf(m_used, mx);
-      // the previous PV MMA must have retired before P is overwritten or O is rescaled
-      if (t > 0) { mbar_wait(p_empty, (uint32_t)((t - 1) & 1)); tc_fence_after(); }
       // lazy rescale: advance the reference maximum only when it grew by more than 2^TAU (P stays
       // <= 2^TAU, harmless in fp32 / bf16), so O is rarely touched.  tcgen05.ld/st are warp-wide
       // (.sync.aligned): the decision is taken per WARP, rows that do not need it scale by 1.
@@ -314,6 +312,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
       const float m_next = want ? m_new : m_used;
       const float alpha = (m_used == -INFINITY) ? 1.0f : ex2f(m_used - m_next);
       const bool touch_o = t > 0 && want && m_used > -INFINITY;
+      l *= alpha;
+      m_used = m_next;
+      const float m_sub = m_used == -INFINITY ? 0.f : m_used;
+      // ---- P = exp2(t - m) -> 16-bit, kept in registers until the previous PV MMA has retired ----
+      const float mul = capped ? 1.0f : p.scale_log2;
+      uint32_t pw[HC / 2];
+#pragma unroll
+      for (int i = 0; i < HC; i += 2) {
+        const float e0 = ex2f(fmaf(sv[i], mul, -m_sub));         // exp2(-inf) = 0 for masked entries
+        const float e1 = ex2f(fmaf(sv[i + 1], mul, -m_sub));
+        l += e0 + e1;
+        if (p.is_fp16) { __half2 h = __floats2half2_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
+        else { __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
+      }
+      // the previous PV MMA must have retired before P is overwritten or O is rescaled
+      if (t > 0) { mbar_wait(p_empty, (uint32_t)((t - 1) & 1)); tc_fence_after(); }
       if (__any_sync(0xffffffffu, touch_o)) {
 #pragma unroll 1
         for (int c0 = 0; c0 < HD; c0 += 32) {
@@ -327,29 +341,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
         }
         tmem_st_wait();
       }
-      l *= alpha;
-      m_used = m_next;
-      const float m_sub = m_used == -INFINITY ? 0.f : m_used;
-      // ---- P = exp2(t - m) -> 16-bit, 128B-swizzled smem; running sum --------------------------
-      const float mul = capped ? 1.0f : p.scale_log2;
-#pragma unroll
-      for (int i = 0; i < HC; ++i) {
-        const float e = ex2f(fmaf(sv[i], mul, -m_sub));          // exp2(-inf) = 0 for masked entries
-        sv[i] = e;
-        l += e;
-      }
 #pragma unroll
       for (int g = 0; g < HC / 8; ++g) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = sv[g * 8 + 2 * j], b = sv[g * 8 + 2 * j + 1];
-          if (p.is_fp16) { __half2 h = __floats2half2_rn(a, b); w[j] = *reinterpret_cast<uint32_t*>(&h); }
-          else { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); w[j] = *reinterpret_cast<uint32_t*>(&h); }
-        }
         const int col = cb + g * 8;                              // column inside the tile
         *reinterpret_cast<uint4*>(p_gen + (col >> 6) * (BM * 128) + swz_off(r, col & 63)) =
-            make_uint4(w[0], w[1], w[2], w[3]);
+            make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
       }
       fence_proxy_async_smem();                   // generic-proxy smem writes -> tensor-core reads
       tc_fence_before();

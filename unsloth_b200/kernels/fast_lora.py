@@ -22,7 +22,7 @@ import os
 import torch
 
 from .. import _lib as L
-from .utils import (GradModeAware, Problem, RANK_BLOCK, gemm_grouped, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
+from .utils import (GradModeAware, Problem, RANK_BLOCK, fused_dequant_enabled, gemm_grouped, gemm_nf4, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
                     keep_dequant, keep_for_backward, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
                     matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
@@ -165,6 +165,8 @@ class _Group:
     def forward(self, keep=False):
         """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None.  `keep`: the
         dequantised weights are private tensors left in `self.dense` for the backward."""
+        if fused_dequant_enabled() and self._fusable():
+            return self._forward_fused_dequant()
         if _fwd_grouped(self.kind):
             return self._forward_grouped(keep)
         X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
@@ -193,6 +195,32 @@ class _Group:
             Y = torch.empty((T, N), dtype=dt, device=dev)
             gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
             outs.append(Y)
+        return outs, XA
+
+    # ---- NF4 expansion fused into the GEMM (csrc/gemm_nf4.cu; prototype behind UB200_FUSED_DEQUANT) --
+    def _fusable(self):
+        for (W, Wq, A, B, s) in self.projs:
+            if Wq is None or type(Wq) is list or W.shape[0] == 1:
+                return False
+            if Wq.blocksize != 64 or Wq.state2.blocksize != 256 or Wq.dtype != self.dtype or self.in_f % 64:
+                return False
+        return self.dtype in (torch.bfloat16, torch.float16)
+
+    def _forward_fused_dequant(self):
+        """No 16-bit copy of W is made: nothing is kept for the backward (it re-dequantises)."""
+        X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
+        XA = None
+        if self.has_lora:
+            XA = gemm(T, self.Rp, [(X2, self.A_cat(refresh=True), self.in_f)],
+                      torch.empty((T, self.Rp), dtype=dt, device=dev))
+        outs = []
+        for off, (W, Wq, A, B, s) in zip(self.offs, self.projs):
+            N = Wq.shape[0]
+            lora = None
+            if A is not None:
+                Bc = B if B.stride(-1) == 1 else B.contiguous()
+                lora = (XA, cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s, refresh=True), self.Rp)
+            outs.append(gemm_nf4(X2, W, Wq, torch.empty((T, N), dtype=dt, device=dev), lora))
         return outs, XA
 
     # ---- grouped execution: ONE persistent launch per phase (csrc/gemm_grouped.cu) ---------------

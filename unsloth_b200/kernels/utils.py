@@ -324,6 +324,36 @@ def gemm_grouped(problems):
     return [pr.out for pr in problems]
 
 
+def fused_dequant_enabled() -> bool:
+    """UB200_FUSED_DEQUANT=1: forward projections expand the NF4 weight inside the GEMM's operand
+    staging (csrc/gemm_nf4.cu) instead of dequantising to a 16-bit buffer first.  Measured trade-off in
+    DESIGN.md section 4.2; default off."""
+    return os.environ.get("UB200_FUSED_DEQUANT", "0") == "1"
+
+
+def gemm_nf4(X2, W, quant_state, out, lora=None):
+    """out[T, N] = X2[T, K] @ dequant(W)^T (+ XA @ B_pad^T): NF4 expansion fused into the tcgen05 GEMM.
+    lora: None or (XA [T, Rp], B_pad [N, Rp] scaled, Rp)."""
+    absmax, shape, dtype, blocksize, offset, absmax2, code2, blocksize2 = _unpack_quant_state(quant_state)
+    if not torch.is_tensor(offset):
+        offset = torch.tensor(float(offset), dtype=torch.float32, device=W.device)
+    T, K = X2.shape
+    N = shape[0]
+    xa, bp, rk = (None, None, 0) if lora is None else lora
+    ev = GEMM_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("ub200_gemm_nf4", T, N, K, L.ptr(X2), X2.stride(0), L.ptr(W), L.ptr(absmax), L.ptr(code2),
+           L.ptr(absmax2), L.ptr(offset), int(blocksize), int(blocksize2), L.ptr(xa),
+           0 if xa is None else xa.stride(0), L.ptr(bp), 0 if bp is None else bp.stride(0), int(rk),
+           L.ptr(out), out.stride(0), L.dt(out), L.stream())
+    if ev is not None:
+        e1.record()
+        ev.append((2.0 * T * N * K, e0, e1, {"kernel": "gemm_nf4"}))
+    return out
+
+
 def cast_pad(src, dst, row_off=0, col_off=0, scale=1.0, transpose=False):
     """dst (2-D, fully overwritten) <- zeros with scale*src (optionally transposed) placed at
     (row_off, col_off)."""

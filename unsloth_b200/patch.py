@@ -149,6 +149,9 @@ def LlamaAttention_fast_forward(self, hidden_states, cos, sin, position_ids=None
     Q = Q.view(bsz, q_len, n_heads, hd).transpose(1, 2)                 # views, no copies
     Kt = Kt.view(bsz, q_len, n_kv, hd).transpose(1, 2)
     Q, Kt = K.fast_rope_embedding(Q, Kt, cos, sin, position_ids)        # llama.py:730, in place
+    sink = getattr(self, "_ub_kv_sink", None)
+    if sink is not None:        # prefill of generate(): keep the rotated K and V for the KV cache
+        sink.append((Kt.detach(), V.view(bsz, q_len, n_kv, hd).transpose(1, 2).detach()))
     window = (-1, -1)
     sw = self._ub_window
     longest = q_len if seq_info is None else seq_info[2]
@@ -211,9 +214,18 @@ def Model_fast_forward(self, input_ids, position_ids=None, packed_seq_lengths=No
     # reference's use_gradient_checkpointing, models/llama.py:1169-1192; no activation offload):
     # not needed for the BASELINE configs on a 180 GB B200, available for longer sequences
     ckpt = getattr(self, "_ub_gradient_checkpointing", False) and torch.is_grad_enabled()
-    if ckpt:
+    if ckpt == "unsloth" and seq_len < 512:       # _utils.py:360-386: offloading pays from ~512 tokens
+        ckpt = True
+    if ckpt == "unsloth":
+        from .checkpoint import offloaded_checkpoint
+
+        def checkpoint(fn, layer, hidden, *rest, **kw):              # fn = DecoderLayer_fast_forward
+            return offloaded_checkpoint(lambda h, *r: fn(layer, h, *r), hidden, *rest)
+    elif ckpt:
         from torch.utils.checkpoint import checkpoint
-    if self._ub_gemma or not FUSE_ADD_NORM:
+    if self._ub_gemma or not FUSE_ADD_NORM or ckpt == "unsloth":
+        # (offloaded checkpoints keep exactly ONE tensor per layer: the layer-by-layer form, whose
+        # only live input is the hidden state)
         for layer in self.layers:
             if ckpt:
                 h = checkpoint(DecoderLayer_fast_forward, layer, h, cos, sin, idx, seq_info,
@@ -285,10 +297,12 @@ def _arch_of(model):
     return mt
 
 
-def install(model, gradient_checkpointing=False):
+def install(model, gradient_checkpointing=False, tiled_mlp=0):
     """Rebind a HuggingFace Llama / Mistral / Gemma-2 CausalLM (with LoRA-wrapped projections)
-    onto the unsloth_b200 kernels.  Returns the model.  `gradient_checkpointing`: recompute each
-    decoder layer in the backward (off by default: the BASELINE configs fit a B200 without)."""
+    onto the unsloth_b200 kernels.  Returns the model.  `gradient_checkpointing`: False (default: the
+    BASELINE configs fit a B200 without), True (recompute each decoder layer in the backward) or
+    "unsloth" (the same with the layer inputs offloaded to pinned host memory); `tiled_mlp` = n > 1:
+    the MLP runs over n token shards and is recomputed shard-wise (checkpoint.py)."""
     arch = _arch_of(model)
     cfg = model.config
     gemma = arch == "gemma2"
@@ -306,7 +320,8 @@ def install(model, gradient_checkpointing=False):
     inner._ub_rotary = RotaryCache(hd, float(rope_theta or 10000.0), dev,
                                    torch.float32 if gemma else dtype, rope_scaling)
     inner._ub_gemma = gemma
-    inner._ub_gradient_checkpointing = bool(gradient_checkpointing)
+    inner._ub_gradient_checkpointing = gradient_checkpointing if gradient_checkpointing == "unsloth" \
+        else bool(gradient_checkpointing)
     if gradient_checkpointing:
         # per-layer recompute owns the memory: do not keep 16-bit expansions alive across layers
         from .kernels import utils as _KU
@@ -326,6 +341,10 @@ def install(model, gradient_checkpointing=False):
             attn._ub_softcap = 0.0
             attn._ub_window = getattr(cfg, "sliding_window", None) if arch == "mistral" else None
         layer.mlp.forward = types.MethodType(mlp_fn, layer.mlp)                      # llama.py:3725
+        if tiled_mlp and tiled_mlp > 1:                                              # llama.py:3719-3723
+            from .checkpoint import tiled_mlp_forward
+            layer.mlp._unsloth_forward = layer.mlp.forward
+            layer.mlp.forward = tiled_mlp_forward(layer.mlp._unsloth_forward, int(tiled_mlp))
         attn.apply_qkv = K.apply_lora_qkv                                            # llama.py:3748
         attn.apply_o = K.apply_lora_o                                                # llama.py:3766
     model.forward = types.MethodType(CausalLM_fast_forward, model)
@@ -364,7 +383,7 @@ def attach_qlora(model, r=16, lora_alpha=16, init_b_std=0.0, quantize=True):
 
 def build_qlora_model(name="llama-3-8b", r=16, lora_alpha=16, device="cuda", dtype=torch.bfloat16,
                       seed=3407, init_b_std=0.0, num_hidden_layers=None, quantize=True,
-                      gradient_checkpointing=False, **overrides):
+                      gradient_checkpointing=False, tiled_mlp=0, **overrides):
     """Random-init model of a BASELINE.json config on `device`, NF4 + LoRA, kernels installed."""
     from transformers import AutoModelForCausalLM
     cfg = hf_config(name, num_hidden_layers, **overrides)
@@ -379,4 +398,4 @@ def build_qlora_model(name="llama-3-8b", r=16, lora_alpha=16, device="cuda", dty
     model.to(dtype)
     attach_qlora(model, r=r, lora_alpha=lora_alpha, init_b_std=init_b_std, quantize=quantize)
     torch.cuda.empty_cache()
-    return install(model, gradient_checkpointing=gradient_checkpointing)
+    return install(model, gradient_checkpointing=gradient_checkpointing, tiled_mlp=tiled_mlp)
