@@ -279,8 +279,8 @@ int ub200_attention_fwd(const void* Q, const void* K, const void* V, void* O, fl
 /* Backward of ub200_attention_fwd: dQ [tokens, Hq*D], dK / dV [tokens, Hk*D] (contiguous) from dO, the
  * forward's O (contiguous [tokens, Hq*D]) and lse.  `delta` is caller-provided fp32 scratch shaped
  * like lse.  P is recomputed; dK/dV are accumulated per key tile over all query heads of the group
- * and dQ per query tile, both in TMEM -- no atomics, run-to-run bit-identical.  D in {64, 128}
- * (D = 256 would need 768 TMEM columns: UB200_ERR_UNSUPPORTED).                                    */
+ * and dQ per query tile, both in TMEM -- no atomics, run-to-run bit-identical.  D in {64, 128, 256}
+ * (D = 256: dV and dK in two passes, since dK + dV + score tiles exceed the 512 TMEM columns).     */
 int ub200_attention_bwd(const void* dO, const void* Q, const void* K, const void* V, const void* O,
                         const float* lse, float* delta, void* dQ, void* dK, void* dV,
                         const int32_t* cu_seqlens, int n_docs, int max_seqlen, int batch, int seqlen,

@@ -485,30 +485,48 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const T* __restrict__ O
   }
 }
 
-template <int D, bool DKV>
+// MODE 0: dK and dV together (D <= 128)      owner K, V    stream Q, dO    tiles P^T, dS^T
+// MODE 1: dQ                                   owner Q, dO   stream K, V     tile  dS
+// MODE 2: dV only  (D = 256: dK + dV + the score tiles would need 768 TMEM columns)   tile P^T
+// MODE 3: dK only  (D = 256)                                                          tile dS^T
+enum { BWD_DKV = 0, BWD_DQ = 1, BWD_DV = 2, BWD_DK = 3 };
+
+template <int D, int MODE>
 struct BwdCfg {
   static constexpr int DB = D / 64;
+  static constexpr bool KEYS_OWN = MODE != BWD_DQ;                   // owner rows are keys (lanes = keys)
+  static constexpr int NOWN = MODE == BWD_DV ? 1 : 2;                // resident owner operands
+  static constexpr int NKIND = MODE == BWD_DV ? 1 : 2;               // score MMAs per unit (S | S and dP)
+  static constexpr int NT = MODE == BWD_DKV ? 2 : 1;                 // produced 16-bit tiles per unit
+  static constexpr int NACC = MODE == BWD_DKV ? 2 : 1;               // accumulators
+  static constexpr bool WANT_P = MODE == BWD_DKV || MODE == BWD_DV;
+  static constexpr bool WANT_DS = MODE != BWD_DV;
+  // D = 256: two resident [128 x 256] operands already take 128 KB -> single-stage stream / tile
+  static constexpr int STAGES = (D == 256 && MODE != BWD_DV) ? 1 : 2;
+  static constexpr int TBUF = D == 256 ? 1 : 2;
   static constexpr uint32_t OWN_BYTES = (uint32_t)DB * 128 * 128;    // one owner operand [128 x D]
   static constexpr uint32_t STR_BYTES = (uint32_t)DB * BU * 128;     // one streamed operand [64 x D]
   static constexpr uint32_t T_BYTES = 128 * 128;                     // one 16-bit [128 x 64] operand tile
-  static constexpr int NT = DKV ? 2 : 1;                             // produced tiles per unit (P^T and dS^T | dS)
-  static constexpr uint32_t SMEM_BYTES = 2 * OWN_BYTES + 2 * 2 * STR_BYTES + 2 * NT * T_BYTES + 1024 + 256 + 2048;
+  static constexpr uint32_t SMEM_BYTES = NOWN * OWN_BYTES + STAGES * 2 * STR_BYTES + TBUF * NT * T_BYTES + 1024 + 256 + 2048;
   static constexpr uint32_t TMEM_SC = 0;                             // score buffers: [2 units][2 kinds] x 64 columns
-  static constexpr uint32_t TMEM_ACC = 256;                          // accumulators: D (dQ | dK) + D (dV)
+  static constexpr uint32_t TMEM_ACC = 256;                          // accumulators: NACC x D columns
   static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(256 + NACC * D <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int D, bool DKV>
+template <int D, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_constant__ BwdParams p) {
-  using C = BwdCfg<D, DKV>;
+  using C = BwdCfg<D, MODE>;
+  constexpr bool DKV = C::KEYS_OWN;               // owner rows are keys, per-column scalars come from the queries
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t own_smem = smem_base;                               // own1 | own2
-  const uint32_t str_smem = own_smem + 2 * C::OWN_BYTES;             // stage s: str1 | str2
-  const uint32_t t_smem = str_smem + 2 * 2 * C::STR_BYTES;           // buffer b: tile0 (| tile1)
+  const uint32_t str_smem = own_smem + C::NOWN * C::OWN_BYTES;       // stage s: str1 | str2
+  const uint32_t t_smem = str_smem + C::STAGES * 2 * C::STR_BYTES;   // buffer b: tile0 (| tile1)
   uint8_t* t_gen = smem_gen + (t_smem - smem_base);
-  const uint32_t bar_base = t_smem + 2 * C::NT * C::T_BYTES;
+  const uint32_t bar_base = t_smem + C::TBUF * C::NT * C::T_BYTES;
   // barriers: own_full, str_full[2], str_empty[2], sc_full[2], t_full[2], t_empty[2], out_full
   const uint32_t own_full = bar_base;
   auto str_full = [&](int s) { return bar_base + 8u * (1 + s); };
@@ -583,17 +601,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
   if (warp == 0) {
     // ================================ TMA producer ===================================
     if (elect_one()) {
-      mbar_expect_tx(own_full, 2 * C::OWN_BYTES);
+      mbar_expect_tx(own_full, C::NOWN * C::OWN_BYTES);
 #pragma unroll
       for (int b = 0; b < C::DB; ++b) {
         tma_load_2d(own_smem + b * (128 * 128), &p.tmap_own1, own_full, own_col1 + b * 64, seq_start + o0);
-        tma_load_2d(own_smem + C::OWN_BYTES + b * (128 * 128), &p.tmap_own2, own_full, own_col1 + b * 64, seq_start + o0);
+        if (C::NOWN == 2)
+          tma_load_2d(own_smem + C::OWN_BYTES + b * (128 * 128), &p.tmap_own2, own_full, own_col1 + b * 64, seq_start + o0);
       }
     }
     __syncwarp();
     for (int u = 0; u < n_units; ++u) {
-      const int st = u & 1;
-      mbar_wait(str_empty(st), (uint32_t)(((u >> 1) & 1) ^ 1));
+      const int st = u % C::STAGES;
+      mbar_wait(str_empty(st), (uint32_t)(((u / C::STAGES) & 1) ^ 1));
       const uint32_t s1 = str_smem + st * 2 * C::STR_BYTES, s2 = s1 + C::STR_BYTES;
       const int col = str_col(u), row = seq_start + unit_row0(u);
       if (elect_one()) {
@@ -611,15 +630,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
     const uint32_t idesc_sc = make_idesc(128, BU, 0, 0, p.is_fp16);        // scores: both K-major over D
     const uint32_t idesc_acc = make_idesc(128, D, 0, 1, p.is_fp16);        // accumulate: tile K-major (64), streamed operand MN-major
     auto issue_scores = [&](int u) {
-      const int st = u & 1;
-      mbar_wait(str_full(st), (uint32_t)((u >> 1) & 1));
+      const int st = u % C::STAGES, sb = u & 1;
+      mbar_wait(str_full(st), (uint32_t)((u / C::STAGES) & 1));
       tc_fence_after();
       const uint32_t s1 = str_smem + st * 2 * C::STR_BYTES, s2 = s1 + C::STR_BYTES;
       if (elect_one()) {
 #pragma unroll
-        for (int kind = 0; kind < 2; ++kind) {
+        for (int kind = 0; kind < C::NKIND; ++kind) {
           const uint32_t a_base = own_smem + kind * C::OWN_BYTES, b_base = kind ? s2 : s1;
-          const uint32_t d_tmem = tmem_base + C::TMEM_SC + (uint32_t)(st * 128 + kind * 64);
+          const uint32_t d_tmem = tmem_base + C::TMEM_SC + (uint32_t)(sb * 128 + kind * 64);
 #pragma unroll
           for (int b = 0; b < C::DB; ++b) {
             const uint64_t da = make_smem_desc(a_base + b * (128 * 128), 16u, 1024u);
@@ -629,7 +648,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
               umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_sc, (b > 0 || k > 0) ? 1u : 0u);
           }
         }
-        umma_commit(sc_full(st));
+        umma_commit(sc_full(sb));
       }
       __syncwarp();
     };
@@ -637,14 +656,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
     tc_fence_after();
     if (n_units > 0) issue_scores(0);
     for (int u = 0; u < n_units; ++u) {
-      const int st = u & 1;
-      if (u + 1 < n_units) issue_scores(u + 1);
-      mbar_wait(t_full(st), (uint32_t)((u >> 1) & 1));
+      const int st = u % C::STAGES, tbi = u % C::TBUF;
+      if (C::STAGES == 2 && u + 1 < n_units) issue_scores(u + 1);     // next unit's scores ahead of this unit's accumulation
+      mbar_wait(t_full(tbi), (uint32_t)((u / C::TBUF) & 1));
       tc_fence_after();
       const uint32_t s1 = str_smem + st * 2 * C::STR_BYTES, s2 = s1 + C::STR_BYTES;
-      const uint32_t tb = t_smem + st * C::NT * C::T_BYTES;
+      const uint32_t tb = t_smem + tbi * C::NT * C::T_BYTES;
       if (elect_one()) {
-        if (DKV) {
+        if (MODE == BWD_DKV) {
           // dV += P^T (tile 0) x dO_u (str2, MN-major);  dK += dS^T (tile 1) x Q_u (str1, MN-major)
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
@@ -656,19 +675,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
               umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc_acc, (u > 0 || k > 0) ? 1u : 0u);
           }
         } else {
-          // dQ += dS (tile 0) x K_u (str1, MN-major)
+          // dQ += dS x K_u (str1) | dV += P^T x dO_u (str2) | dK += dS^T x Q_u (str1): streamed operand MN-major
           const uint64_t da = make_smem_desc(tb, 16u, 1024u);
-          const uint64_t db = make_smem_desc(s1, (uint32_t)(BU * 128), 1024u);
+          const uint64_t db = make_smem_desc(MODE == BWD_DV ? s2 : s1, (uint32_t)(BU * 128), 1024u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base + C::TMEM_ACC, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc_acc,
                      (u > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(str_empty(st));
-        umma_commit(t_empty(st));
+        umma_commit(t_empty(tbi));
         if (u == n_units - 1) umma_commit(out_full);
       }
       __syncwarp();
+      if (C::STAGES == 1 && u + 1 < n_units) issue_scores(u + 1);     // single stage: only after it has been refilled
     }
   } else {
     // ================================ compute warps ==================================
@@ -706,7 +726,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
       if (cw < 128) vec[cw] = pre;                // buffer 0: [lse2 64 | delta 64]
     }
     for (int u = 0; u < n_units; ++u) {
-      const int st = u & 1;
+      const int st = u & 1;                       // score buffer / scalar buffer
+      const int tbi = u % C::TBUF;
       if (DKV) {
         prefetch_vec(u + 1);
         asm volatile("bar.sync 5, 256;" ::: "memory");          // vec[st] visible; vec[st^1] free
@@ -714,13 +735,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
       const int u0 = unit_row0(u);
       mbar_wait(sc_full(st), (uint32_t)((u >> 1) & 1));
       tc_fence_after();
-      mbar_wait(t_empty(st), (uint32_t)(((u >> 1) & 1) ^ 1));   // tiles of unit u-2 consumed
+      mbar_wait(t_empty(tbi), (uint32_t)(((u / C::TBUF) & 1) ^ 1));   // this tile buffer's previous use consumed
       const int cb = ch * 32;
       uint32_t sraw[32], draw[32];
       tmem_ld32(tmem_base + lane_addr + C::TMEM_SC + (uint32_t)(st * 128 + cb), sraw);
-      tmem_ld32(tmem_base + lane_addr + C::TMEM_SC + (uint32_t)(st * 128 + 64 + cb), draw);
+      if (C::WANT_DS) tmem_ld32(tmem_base + lane_addr + C::TMEM_SC + (uint32_t)(st * 128 + 64 + cb), draw);
       tmem_ld_wait(sraw);
-      tmem_ld_wait(draw);
+      if (C::WANT_DS) tmem_ld_wait(draw);
       // visibility: query i sees key j iff j <= i, i - j <= window, both inside the sequence
       const bool need_mask = DKV ? ((u0 < o0 + 127) || (p.window >= 0 && u0 + BU - 1 - o0 > p.window) ||
                                     (u0 + BU > seq_len) || (o0 + 128 > seq_len))
@@ -746,8 +767,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
             const bool vis = (kj <= qi) && (p.window < 0 || qi - kj <= p.window) && (qi < seq_len) && (kj < seq_len);
             if (!vis) pe = 0.f;
           }
-          float ds = pe * (__uint_as_float(draw[i + e]) - dl) * p.scale;
-          if (capped) ds *= (1.0f - th * th);
+          float ds = 0.f;
+          if (C::WANT_DS) {
+            ds = pe * (__uint_as_float(draw[i + e]) - dl) * p.scale;
+            if (capped) ds *= (1.0f - th * th);
+          }
           pv[e] = pe; dv[e] = ds;
         }
         if (p.is_fp16) {
@@ -758,13 +782,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
           __nv_bfloat162 g = __floats2bfloat162_rn(dv[0], dv[1]); dw[i >> 1] = *reinterpret_cast<uint32_t*>(&g);
         }
       }
-      uint8_t* tb = t_gen + st * C::NT * C::T_BYTES;
+      uint8_t* tb = t_gen + tbi * C::NT * C::T_BYTES;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint32_t off = swz_off(r, cb + g * 8);
-        if (DKV) {
+        if (MODE == BWD_DKV) {
           *reinterpret_cast<uint4*>(tb + off) = make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
           *reinterpret_cast<uint4*>(tb + C::T_BYTES + off) = make_uint4(dw[4 * g], dw[4 * g + 1], dw[4 * g + 2], dw[4 * g + 3]);
+        } else if (MODE == BWD_DV) {
+          *reinterpret_cast<uint4*>(tb + off) = make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
         } else {
           *reinterpret_cast<uint4*>(tb + off) = make_uint4(dw[4 * g], dw[4 * g + 1], dw[4 * g + 2], dw[4 * g + 3]);
         }
@@ -772,14 +798,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
       if (DKV && cw < 128) vec[(st ^ 1) * 128 + cw] = pre;      // next unit's scalars
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(t_full(st));
+      mbar_arrive(t_full(tbi));
     }
     // ---- epilogue: accumulators -> 16-bit rows -------------------------------------------------
     if (n_units > 0) { mbar_wait(out_full, 0); tc_fence_after(); }
     const bool row_ok = own_pos < seq_len;
     constexpr int HD = D / 2;
 #pragma unroll 1
-    for (int which = 0; which < (DKV ? 2 : 1); ++which) {
+    for (int which = 0; which < C::NACC; ++which) {
       uint16_t* orow = reinterpret_cast<uint16_t*>(which == 0 ? p.out1 : p.out2) +
                        (int64_t)(seq_start + own_pos) * (which == 0 ? p.ld_out1 : p.ld_out2) + (int64_t)own_head * D + ch * HD;
 #pragma unroll 1
@@ -817,17 +843,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
   }
 }
 
-template <int D, bool DKV>
+template <int D, int MODE>
 static int launch_bwd(const BwdParams& p, dim3 grid, cudaStream_t st) {
-  using C = BwdCfg<D, DKV>;
+  using C = BwdCfg<D, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  attn_bwd_kernel<D, DKV><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  attn_bwd_kernel<D, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
   return UB200_OK;
 }
 
@@ -844,7 +870,7 @@ extern "C" int ub200_attention_bwd(const void* dO, const void* Q, const void* K,
   using namespace ub;
   using namespace ub::attn;
   if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_BAD_ARG;
-  if (head_dim != 64 && head_dim != 128) return UB200_ERR_UNSUPPORTED;      // D = 256 needs 768 TMEM columns
+  if (head_dim != 64 && head_dim != 128 && head_dim != 256) return UB200_ERR_UNSUPPORTED;
   if (n_heads_q % n_heads_k) return UB200_ERR_BAD_ARG;
   const int64_t tokens = (int64_t)batch * seqlen;
   if (tokens <= 0) return UB200_OK;
@@ -881,7 +907,15 @@ extern "C" int ub200_attention_bwd(const void* dO, const void* Q, const void* K,
   p.out1 = dK; p.out2 = dV; p.ld_out1 = ldk; p.ld_out2 = ldk;
   {
     dim3 grid((longest + 127) / 128, n_heads_k, nb);
-    rc = head_dim == 64 ? launch_bwd<64, true>(p, grid, stream) : launch_bwd<128, true>(p, grid, stream);
+    if (head_dim == 256) {
+      // dK + dV + score tiles would need 768 TMEM columns: two passes over the key tile
+      p.out1 = dV;
+      if ((rc = launch_bwd<256, BWD_DV>(p, grid, stream))) return rc;
+      p.out1 = dK;
+      rc = launch_bwd<256, BWD_DK>(p, grid, stream);
+    } else {
+      rc = head_dim == 64 ? launch_bwd<64, BWD_DKV>(p, grid, stream) : launch_bwd<128, BWD_DKV>(p, grid, stream);
+    }
     if (rc) return rc;
   }
   // ---- dQ: owner = Q, dO tiles; stream = K, V units ------------------------------------------------
@@ -892,7 +926,8 @@ extern "C" int ub200_attention_bwd(const void* dO, const void* Q, const void* K,
   p.out1 = dQ; p.out2 = nullptr; p.ld_out1 = ldq; p.ld_out2 = 0;
   {
     dim3 grid((longest + 127) / 128, n_heads_q, nb);
-    rc = head_dim == 64 ? launch_bwd<64, false>(p, grid, stream) : launch_bwd<128, false>(p, grid, stream);
+    rc = head_dim == 64 ? launch_bwd<64, BWD_DQ>(p, grid, stream)
+         : head_dim == 128 ? launch_bwd<128, BWD_DQ>(p, grid, stream) : launch_bwd<256, BWD_DQ>(p, grid, stream);
     if (rc) return rc;
   }
   UB_RETURN_LAST();

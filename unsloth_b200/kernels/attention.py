@@ -8,8 +8,8 @@ projection buffers (GQA native, no copies), returns [B, S, Hq, D]:
   * forward: csrc/attention.cu `ub200_attention_fwd` (TMA + tcgen05 + TMEM, exp2 online softmax,
     window / softcap / packed rows) saving the row log-sum-exp;
   * backward: csrc/attention.cu `ub200_attention_bwd` (dK/dV and dQ kernels, recompute of P from the
-    saved LSE, deterministic: no atomics) for D = 64 / 128; D = 256 uses flash-attn 2's backward on
-    our (O, LSE).
+    saved LSE, deterministic: no atomics); D = 256 (Gemma-2) runs dV and dK as two passes because
+    dK + dV + the score tiles would need 768 of the 512 TMEM columns.
 """
 from __future__ import annotations
 
@@ -65,8 +65,7 @@ def attention_forward(Q, K, V, softmax_scale, window_left=-1, softcap=0.0, seq_i
 
 
 def _bwd_library(dO, Q, K, V, O, lse, softmax_scale, window_left, softcap, seq_info):
-    """TRANSITIONAL: flash-attn 2's backward on our forward's (O, LSE) while the tcgen05 backward is
-    being validated (UB200_ATTN_BWD=library)."""
+    """A/B only (UB200_ATTN_BWD=library): flash-attn 2's backward on our forward's (O, LSE)."""
     from flash_attn.flash_attn_interface import _wrapped_flash_attn_backward, _wrapped_flash_attn_varlen_backward
     B, S, Hq, D = Q.shape
     Qc, Kc, Vc = (t.contiguous() for t in (Q, K, V))
@@ -86,9 +85,7 @@ def _bwd_library(dO, Q, K, V, O, lse, softmax_scale, window_left, softcap, seq_i
 
 def attention_backward(dO, Q, K, V, O, lse, softmax_scale, window_left=-1, softcap=0.0, seq_info=None):
     B, S, Hq, D = Q.shape
-    if os.environ.get("UB200_ATTN_BWD", "own") == "library" or D == 256:
-        # D = 256 (Gemma-2): dK + dV + the score tiles need 768 TMEM columns; the library backward
-        # runs on our forward's (O, LSE) until a split-D variant exists
+    if os.environ.get("UB200_ATTN_BWD", "own") == "library":
         return _bwd_library(dO, Q, K, V, O, lse, softmax_scale, window_left, softcap, seq_info)
     Hk = K.shape[2]
     Q, qs = _as_token_rows(Q)
