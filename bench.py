@@ -313,6 +313,9 @@ def run_ours(args):
         KU.GEMM_EVENTS = [] if leg == "profile" else None
         torch.cuda.reset_peak_memory_stats()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        prof = leg == "resident" and os.environ.get("UB200_PROFILE_RANGE", "0") == "1"
+        if prof:        # `ncu --profile-from-start off`: only the timed steps are profiled (never a bench value)
+            torch.cuda.cudart().cudaProfilerStart()
         s.record()
         loss = None
         for i in range(args.warmup, total_steps):
@@ -326,6 +329,8 @@ def run_ours(args):
                 loss = step_fn(dev_ids[i], dev_lab[i])
         e.record()
         barrier()
+        if prof:
+            torch.cuda.cudart().cudaProfilerStop()
         ms = s.elapsed_time(e)
         if world > 1:
             t = torch.tensor([ms], device=dev)

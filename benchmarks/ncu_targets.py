@@ -65,5 +65,34 @@ elif name == "ce":
     for _ in range(3):
         l, lse = _ce_forward(logits, labels, 0.0, 0.0)
         _ce_backward_(logits, lse, labels, dl, 0, 0.0, 0.0)
+elif name in ("attn_fwd", "attn_bwd"):
+    from unsloth_b200.kernels.attention import attention_backward, attention_forward
+    B, S, Hq, Hk, D = 4, 2048, 32, 8, 128
+    q = torch.randn(B, S, Hq * D, device=DEV, dtype=BF).view(B, S, Hq, D)
+    k = torch.randn(B, S, Hk * D, device=DEV, dtype=BF).view(B, S, Hk, D)
+    v = torch.randn(B, S, Hk * D, device=DEV, dtype=BF).view(B, S, Hk, D)
+    for _ in range(2):
+        O, lse = attention_forward(q, k, v, D ** -0.5)
+    if name == "attn_bwd":
+        dO = torch.randn_like(O)
+        for _ in range(2):
+            attention_backward(dO, q, k, v, O, lse, D ** -0.5)
+elif name == "grouped":
+    from unsloth_b200.nf4 import quantize_nf4
+    os.environ["UB200_GROUPED_BWD"] = "1"
+    r = 16
+    X = torch.randn(4, 2048, H, device=DEV).to(BF)
+
+    def mk(o, i):
+        p_, q_ = quantize_nf4((torch.randn(o, i, device=DEV) * 0.02).to(BF))
+        return p_, q_, torch.nn.Parameter((torch.rand(r, i, device=DEV) * 2 - 1) / i ** 0.5), \
+            torch.nn.Parameter(torch.randn(o, r, device=DEV) * 0.02)
+    qp, kp, vp = mk(H, H), mk(1024, H), mk(1024, H)
+    dY = (torch.randn(4, 2048, H, device=DEV) * 0.1).to(BF)
+    for _ in range(2):
+        x = X.clone().requires_grad_()
+        o = K.LoRA_QKV.apply(x, qp[0], qp[1], qp[2], qp[3], 1.0, kp[0], kp[1], kp[2], kp[3], 1.0,
+                             vp[0], vp[1], vp[2], vp[3], 1.0, True)
+        torch.autograd.backward(list(o), [dY, dY[..., :1024].contiguous(), dY[..., :1024].contiguous()])
 torch.cuda.synchronize()
 print("ok")

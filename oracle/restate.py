@@ -559,3 +559,45 @@ def matmul_lora_truth(X, Wd, A, B, s):
     if A is not None:
         out = out + s * (X2 @ A.double().t()) @ B.double().t()
     return out.reshape(*X.shape[:-1], -1)
+
+
+# --------------------------------------------------------------------------------------
+# attention between RoPE and apply_o  (utils/attention_dispatch.py:298-617; the reference calls
+# flash-attn / xformers / SDPA -- all compute the masked softmax below)
+# --------------------------------------------------------------------------------------
+
+
+def attention(Q, K, V, scale, window_left=-1, softcap=0.0, lengths=None):
+    """fp32 definition of what the reference's attention backends compute for training:
+    causal, optional sliding window as flash-attn's `window_size=(w, w)` under causal masking
+    (key j visible to query i iff i - w <= j <= i; mistral.py:112-128, gemma2.py:139-150), optional
+    tanh soft-capping of the scaled scores (gemma2.py:152-199), block-diagonal over the documents
+    of a packed row (`lengths`, attention_dispatch.py:433-447).
+    Q [B,S,Hq,D], K / V [B,S,Hk,D] -> (O [B,S,Hq,D] fp32, lse [B,Hq,S] | [Hq, B*S] for packed rows)."""
+    B, S, Hq, D = Q.shape
+    rep = Hq // K.shape[2]
+    q = Q.float().permute(0, 2, 1, 3)
+    k = K.float().permute(0, 2, 1, 3).repeat_interleave(rep, 1)
+    v = V.float().permute(0, 2, 1, 3).repeat_interleave(rep, 1)
+    if lengths is not None:
+        q, k, v = (t.permute(1, 0, 2, 3).reshape(1, Hq, B * S, D) for t in (q, k, v))
+    n = q.shape[2]
+    s = (q @ k.transpose(-1, -2)) * scale
+    if softcap:
+        s = softcap * torch.tanh(s / softcap)
+    i = torch.arange(n, device=Q.device)[:, None]
+    j = torch.arange(n, device=Q.device)[None, :]
+    mask = j <= i
+    if window_left >= 0:
+        mask = mask & (j >= i - window_left)
+    if lengths is not None:
+        doc = torch.repeat_interleave(torch.arange(len(lengths), device=Q.device),
+                                      torch.as_tensor(lengths, device=Q.device))
+        mask = mask & (doc[:, None] == doc[None, :])
+    s = s.masked_fill(~mask, float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    o = torch.softmax(s, -1) @ v
+    if lengths is not None:
+        o = o.reshape(Hq, B, S, D).permute(1, 0, 2, 3)
+        return o.permute(0, 2, 1, 3), lse.reshape(Hq, B * S)
+    return o.permute(0, 2, 1, 3), lse

@@ -12,32 +12,9 @@ DEV, BF = "cuda", torch.bfloat16
 
 
 def ref_attention(Q, K, V, scale, window_left=-1, softcap=0.0, lengths=None):
-    """fp32 definition.  Q [B,S,Hq,D] ... returns (O [B,S,Hq,D] fp32, lse [B,Hq,S])."""
-    B, S, Hq, D = Q.shape
-    rep = Hq // K.shape[2]
-    q = Q.float().permute(0, 2, 1, 3)
-    k = K.float().permute(0, 2, 1, 3).repeat_interleave(rep, 1)
-    v = V.float().permute(0, 2, 1, 3).repeat_interleave(rep, 1)
-    if lengths is not None:                       # packed: one row of B*S tokens
-        q, k, v = (t.permute(1, 0, 2, 3).reshape(1, Hq, B * S, D) for t in (q, k, v))
-    n = q.shape[2]
-    s = (q @ k.transpose(-1, -2)) * scale
-    if softcap:
-        s = softcap * torch.tanh(s / softcap)
-    i, j = torch.arange(n, device=Q.device)[:, None], torch.arange(n, device=Q.device)[None, :]
-    mask = j <= i
-    if window_left >= 0:
-        mask = mask & (j >= i - window_left)
-    if lengths is not None:
-        doc = torch.repeat_interleave(torch.arange(len(lengths), device=Q.device), torch.tensor(lengths, device=Q.device))
-        mask = mask & (doc[:, None] == doc[None, :])
-    s = s.masked_fill(~mask, float("-inf"))
-    lse = torch.logsumexp(s, -1)
-    o = torch.softmax(s, -1) @ v
-    if lengths is not None:
-        o = o.reshape(Hq, B, S, D).permute(1, 0, 2, 3)
-        return o.permute(0, 2, 1, 3), lse.reshape(Hq, B * S)
-    return o.permute(0, 2, 1, 3), lse
+    """The oracle's fp32 definition (oracle/restate.py::attention), evaluated on the device."""
+    from oracle import restate as R
+    return R.attention(Q, K, V, scale, window_left, softcap, lengths)
 
 
 def _mk(B, S, Hq, Hk, D, seed=0, strided=True):

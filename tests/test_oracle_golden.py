@@ -290,3 +290,32 @@ def test_fp16_rounding_points_lora(golden):
     _eq16(dX, g["dX"], "dX")
     for mine, key in ((dgA, "d_gA"), (dgB, "d_gB"), (duA, "d_uA"), (duB, "d_uB"), (ddA, "d_dA"), (ddB, "d_dB")):
         _eq16(mine, g[key], key)
+
+
+def test_attention_oracle_vs_torch_sdpa_and_hf_masks():
+    """oracle/restate.py::attention (the definition the GPU attention tests use) against torch's own
+    scaled_dot_product_attention (plain causal, GQA) and against the explicit sliding-window /
+    soft-capping formula of transformers' eager Gemma-2 attention."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    B, S, Hq, Hk, D = 2, 37, 4, 2, 16
+    Q, K, V = torch.randn(B, S, Hq, D), torch.randn(B, S, Hk, D), torch.randn(B, S, Hk, D)
+    O, lse = R.attention(Q, K, V, D ** -0.5)
+    ref = F.scaled_dot_product_attention(Q.transpose(1, 2), K.transpose(1, 2).repeat_interleave(2, 1),
+                                         V.transpose(1, 2).repeat_interleave(2, 1), is_causal=True).transpose(1, 2)
+    torch.testing.assert_close(O, ref, rtol=1e-5, atol=1e-5)
+    # window w: HF masks i - j >= sliding_window, the reference's flash-attn window (w, w) keeps w + 1 keys
+    w, cap = 5, 20.0
+    O2, _ = R.attention(Q, K, V, D ** -0.5, window_left=w, softcap=cap)
+    q, k, v = Q.transpose(1, 2), K.transpose(1, 2).repeat_interleave(2, 1), V.transpose(1, 2).repeat_interleave(2, 1)
+    s = (q @ k.transpose(-1, -2)) * D ** -0.5
+    s = torch.tanh(s / cap) * cap                                    # modeling_gemma2.py eager_attention_forward
+    i, j = torch.arange(S)[:, None], torch.arange(S)[None, :]
+    s = s.masked_fill(~((j <= i) & (i - j < w + 1)), float("-inf"))
+    torch.testing.assert_close(O2, (torch.softmax(s, -1) @ v).transpose(1, 2), rtol=1e-5, atol=1e-5)
+    # packed rows == separate documents
+    lengths = [10, 27]
+    Op, _ = R.attention(Q[:1], K[:1], V[:1], D ** -0.5, lengths=lengths)
+    Oa, _ = R.attention(Q[:1, :10], K[:1, :10], V[:1, :10], D ** -0.5)
+    Ob, _ = R.attention(Q[:1, 10:], K[:1, 10:], V[:1, 10:], D ** -0.5)
+    torch.testing.assert_close(Op, torch.cat([Oa, Ob], 1), rtol=1e-5, atol=1e-5)

@@ -99,7 +99,8 @@ struct FwdCfg {
   static constexpr uint32_t KV_BYTES = (uint32_t)DB * BN * 128;      // one K (or V) tile
   static constexpr uint32_t P_BYTES = (uint32_t)(BN / 64) * BM * 128;
   static constexpr int STAGES = 2;
-  static constexpr uint32_t SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 128 + 2048;
+  static constexpr uint32_t SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + 128 + 2048;   // P double-buffered
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static constexpr uint32_t TMEM_S0 = 0;                             // S buffers: 2 x BN columns
   static constexpr uint32_t TMEM_O = 2 * BN;                         // O: D columns
   static constexpr uint32_t TMEM_COLS = (2 * BN + D) <= 256 ? 256 : 512;
@@ -108,24 +109,29 @@ struct FwdCfg {
 template <int D, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = FwdCfg<D, BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // the swizzled tiles need 1024-byte alignment; the budget has no room for an align-up pad
+  // (224 KB of tiles), so the dynamic segment is declared aligned and checked
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  uint8_t* smem_gen = smem_raw;
   const uint32_t q_smem = smem_base;
   const uint32_t kv_smem = q_smem + C::Q_BYTES;                      // stage s: K at +s*2*KV, V at +KV
   const uint32_t p_smem = kv_smem + C::STAGES * 2 * C::KV_BYTES;
   uint8_t* p_gen = smem_gen + (p_smem - smem_base);
-  const uint32_t bar_base = p_smem + C::P_BYTES;
-  // barriers: q_full, k_full[2], v_full[2], kv_empty[2], s_full[2], p_full, p_empty, o_full
+  const uint32_t bar_base = p_smem + 2 * C::P_BYTES;
+  // barriers: q_full, k_full[2], v_full[2], kv_empty[2], s_full[2], p_full[2], p_empty[2], o_full
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (3 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (5 + s); };
   auto s_full = [&](int s) { return bar_base + 8u * (7 + s); };
-  const uint32_t p_full = bar_base + 8u * 9, p_empty = bar_base + 8u * 10, o_full = bar_base + 8u * 11;
-  const uint32_t tmem_ptr_smem = bar_base + 8u * 12;
+  auto p_full = [&](int s) { return bar_base + 8u * (9 + s); };
+  auto p_empty = [&](int s) { return bar_base + 8u * (11 + s); };
+  const uint32_t o_full = bar_base + 8u * 13;
+  const uint32_t tmem_ptr_smem = bar_base + 8u * 14;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
-  const uint32_t xch_smem = bar_base + 128u;                        // 2 x 2 x 128 floats (row max / sum exchange)
+  const uint32_t xch_smem = bar_base + 128u;                        // 2 x 2 x 128 floats (row max / sum exchange)  [15 barriers + tmem ptr < 128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,7 +166,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
       for (int s = 0; s < 2; ++s) {
         mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(s_full(s), 1);
       }
-      mbar_init(p_full, 256); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(p_full(s), 8); mbar_init(p_empty(s), 1); }   // one arrival per softmax warp
+      mbar_init(o_full, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -228,14 +235,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
     for (int t = 0; t < n_tiles; ++t) {
       const int st = t & 1;
       if (t + 1 < n_tiles) issue_qk(t + 1);
-      mbar_wait(p_full, (uint32_t)(t & 1));
+      mbar_wait(p_full(st), (uint32_t)((t >> 1) & 1));
       mbar_wait(v_full(st), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t vs = kv_smem + st * 2 * C::KV_BYTES + C::KV_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < BN / 64; ++kb) {
-          const uint64_t da = make_smem_desc(p_smem + kb * (BM * 128), 16u, 1024u);
+          const uint64_t da = make_smem_desc(p_smem + st * C::P_BYTES + kb * (BM * 128), 16u, 1024u);
           const uint64_t db = make_smem_desc(vs + kb * 8192u, (uint32_t)(BN * 128), 1024u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                      (t > 0 || kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(kv_empty(st));
-        umma_commit(p_empty);
+        umma_commit(p_empty(st));
         if (t == n_tiles - 1) umma_commit(o_full);
       }
       __syncwarp();
@@ -326,9 +333,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
         if (p.is_fp16) { __half2 h = __floats2half2_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
         else { __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
       }
-      // the previous PV MMA must have retired before P is overwritten or O is rescaled
-      if (t > 0) { mbar_wait(p_empty, (uint32_t)((t - 1) & 1)); tc_fence_after(); }
+      // this P buffer's previous user (the PV MMA of tile t-2) must have retired
+      mbar_wait(p_empty(st), (uint32_t)(((t >> 1) & 1) ^ 1));
       if (__any_sync(0xffffffffu, touch_o)) {
+        // O is rescaled between PV(t-1) and PV(t): wait for PV(t-1) (the other buffer's last commit)
+        mbar_wait(p_empty(st ^ 1), (uint32_t)((((t - 1) >> 1) & 1)));
+        tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < HD; c0 += 32) {
           uint32_t v[32];
@@ -344,12 +354,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
 #pragma unroll
       for (int g = 0; g < HC / 8; ++g) {
         const int col = cb + g * 8;                              // column inside the tile
-        *reinterpret_cast<uint4*>(p_gen + (col >> 6) * (BM * 128) + swz_off(r, col & 63)) =
+        *reinterpret_cast<uint4*>(p_gen + st * C::P_BYTES + (col >> 6) * (BM * 128) + swz_off(r, col & 63)) =
             make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
       }
       fence_proxy_async_smem();                   // generic-proxy smem writes -> tensor-core reads
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();                               // 256 arrivals on one mbarrier serialise: one per warp
+      if (lane == 0) mbar_arrive(p_full(st));
     }
     // ---- epilogue: O / l -> 16-bit rows, LSE ---------------------------------------------------
     {
@@ -584,7 +595,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
       mbar_init(own_full, 1);
       for (int s = 0; s < 2; ++s) {
         mbar_init(str_full(s), 1); mbar_init(str_empty(s), 1); mbar_init(sc_full(s), 1);
-        mbar_init(t_full(s), 256); mbar_init(t_empty(s), 1);
+        mbar_init(t_full(s), 8); mbar_init(t_empty(s), 1);        // one arrival per compute warp
       }
       mbar_init(out_full, 1);
       fence_barrier_init();
@@ -798,7 +809,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
       if (DKV && cw < 128) vec[(st ^ 1) * 128 + cw] = pre;      // next unit's scalars
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(t_full(tbi));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_full(tbi));
     }
     // ---- epilogue: accumulators -> 16-bit rows -------------------------------------------------
     if (n_units > 0) { mbar_wait(out_full, 0); tc_fence_after(); }
