@@ -376,21 +376,23 @@ def run_ours(args):
             a_ = agg.setdefault(info["kernel"], {"flops": 0.0, "ms": 0.0, "n": 0, "rank_flops": 0.0})
             a_["flops"] += fl; a_["ms"] += s_.elapsed_time(e_); a_["n"] += 1
             a_["rank_flops"] += info.get("rank_flops", 0.0)
-        traffic = None
+        traffic_by = {}
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("gemm_kernel_dram_bytes_per_launch")
+            traffic_by = {k: v.get("dram_bytes_per_launch") for k, v in json.load(open(tp)).get("kernels", {}).items()}
         roof_all = []
         for k_, a_ in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
             ach = a_["flops"] / a_["ms"] / 1e9
-            roof_all.append({"bound": "tensor", "kernel": names.get(k_, k_), "achieved": round(ach, 1),
+            roof_all.append({"bound": "tensor", "kernel": names.get(k_, k_), "key": k_, "achieved": round(ach, 1),
                              "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": round(ach / peaks["bf16_tflops_sustained"], 3),
                              "launches_timed": a_["n"], "avg_launch_ms": round(a_["ms"] / a_["n"], 4),
                              "share_of_step": round(a_["ms"] / ms_prof, 3),
                              "rank_block_flops_share": round(a_["rank_flops"] / max(a_["flops"], 1.0), 4)})
         roof = dict(roof_all[0])
-        roof.update({"traffic": traffic, "peak_source": peaks["src"],
+        roof.update({"traffic": traffic_by.get(roof.get("key")), "traffic_note": "ncu dram bytes of ONE representative launch "
+                     "of this kernel (profiles/roofline_traffic.json), not the average over the step's shapes",
+                     "peak_source": peaks["src"],
                      "flops": "algorithmic: 2*M*N*K per product with the TRUE LoRA rank for rank-block segments",
                      "timing": "CUDA-event pair around every launch during an eager pass of the same %d steps "
                                "(%.2f ms/step; events cannot be read inside a replayed graph)" % (args.steps, ms_prof / args.steps)})

@@ -119,15 +119,6 @@ def main():
             with torch.cuda.graph(g):
                 for i in range(reps):
                     K.fast_gemv(x, packs[i % copies], qs, out=out)
-            if "mma" in only:          # experimental round-2 kernel, same graph method
-                from unsloth_b200.kernels.utils import _gemv_nf4
-                o1 = out.view(-1); x1 = x.view(-1)
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
-                    for i in range(reps):
-                        _gemv_nf4(x1, packs[i % copies], qs, o1, _entry="ub200_gemv_nf4_mma")
-                report("gemv_nf4_mma_%dx%d" % (m, k), timeit(g2.replay, iters=10, flush=False) / reps,
-                       bytes_=n * (0.5 + 1 / 64) + 2 * (m + k))
             ms = timeit(g.replay, iters=10, flush=False) / reps
             report("gemv_nf4_%dx%d" % (m, k), ms, bytes_=n * (0.5 + 1 / 64) + 2 * (m + k), copies=copies,
                    timing="cuda graph of %d launches over %d weight copies" % (reps, copies))

@@ -149,16 +149,6 @@ int ub200_gemv_nf4(const void* x, const uint8_t* packed, const float* absmax_f32
                    const float* offset, const float* code16, void* out, int m, int k,
                    int blocksize, int blocksize2, const void* lora_B, int ldb, const float* lora_t,
                    int r, float s, int dtype, cudaStream_t stream);
-/* EXPERIMENTAL -- round-2 candidate for ub200_gemv_nf4 (same contract; k % 64 == 0, blocksize >= 64,
- * k % blocksize == 0): byte pairs looked up as packed 16-bit values and contracted with
- * mma.sync.m16n8k16 (fp32 accumulate), ~3.5 issued instructions per weight instead of ~6.
- * Compiles for sm_100a but was written after the round-1 GPU budget was spent: NOT yet run on
- * hardware and not called by any product path.                                                  */
-int ub200_gemv_nf4_mma(const void* x, const uint8_t* packed, const float* absmax_f32,
-                       const uint8_t* absmax_q, const float* code2, const float* absmax2,
-                       const float* offset, const float* code16, void* out, int m, int k,
-                       int blocksize, int blocksize2, const void* lora_B, int ldb,
-                       const float* lora_t, int r, float s, int dtype, cudaStream_t stream);
 /* 16-bit dense rows: out[m] = W[m,k] . x[k] (`torch.mv(lm_head, h)`, models/llama.py:1460; the
  * LoRA temp A x).  out_dtype F32 or `dtype`.                                                    */
 int ub200_gemv_dense(const void* x, const void* W, int64_t ldw, void* out, int m, int k, int dtype,

@@ -367,30 +367,6 @@ def test_fast_gemv_nf4_vs_oracle_and_bnb_symbol(m, k, dt):
     assert (out2.float() - out.float()).abs().max() <= 8e-3 * out.float().abs().max()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("UB200_RUN_UNVALIDATED", "0") != "1",
-                    reason="experimental mma GEMV: written after the round-1 GPU budget was spent, not "
-                           "yet run on hardware (set UB200_RUN_UNVALIDATED=1)")
-@pytest.mark.parametrize("m,k,dt", [(4096, 4096, torch.bfloat16), (1000, 1024, torch.float16),
-                                    (4096, 14336, torch.bfloat16)])
-def test_experimental_mma_gemv_matches_shipped_gemv(m, k, dt):
-    """ub200_gemv_nf4_mma (round-2 candidate) against the shipped ub200_gemv_nf4 on the same packed
-    weight: the table is rounded to 16 bits there (as bitsandbytes does), so 1-2 output ulps."""
-    from unsloth_b200.kernels.utils import _gemv_nf4
-    from unsloth_b200.nf4 import quantize_nf4
-    torch.manual_seed(m + k)
-    W = (torch.randn(m, k) * 0.02).to(dt).to(DEV)
-    packed, qs = quantize_nf4(W)
-    x = torch.randn(k).to(dt).to(DEV)
-    ref = _gemv_nf4(x, packed, qs, torch.empty(m, dtype=dt, device=DEV))
-    new = _gemv_nf4(x, packed, qs, torch.empty(m, dtype=dt, device=DEV), _entry="ub200_gemv_nf4_mma")
-    assert (new.float() - ref.float()).abs().max() <= 1.6e-2 * ref.float().abs().max()
-    B = (torch.randn(m, 16, device=DEV) * 0.05).to(dt)
-    t = torch.randn(16, device=DEV)
-    ref = _gemv_nf4(x, packed, qs, torch.empty(m, dtype=dt, device=DEV), B, t, 2.0)
-    new = _gemv_nf4(x, packed, qs, torch.empty(m, dtype=dt, device=DEV), B, t, 2.0, _entry="ub200_gemv_nf4_mma")
-    assert (new.float() - ref.float()).abs().max() <= 1.6e-2 * ref.float().abs().max()
-
-
 def test_fast_linear_forward_decode_and_merge_lora():
     """fast_linear_forward (kernels/utils.py:1082-1125) at bsz == q_len == 1 with LoRA in the GEMV
     epilogue, at bsz > 1 through the GEMM, on a dense weight, and `merge_lora` (save.py:620-646):

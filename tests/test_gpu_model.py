@@ -162,9 +162,6 @@ def test_packed_row_equals_separate_documents(name, extra):
     assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.995
 
 
-@pytest.mark.skipif(__import__("os").environ.get("UB200_RUN_UNVALIDATED", "0") != "1",
-                    reason="written after the round-1 GPU budget was spent; not yet run on hardware "
-                           "(set UB200_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("name,extra", [("llama-3-8b", {}), ("gemma-2-9b", {"query_pre_attn_scalar": 64})])
 def test_return_logits_path_matches_fused_ce(name, extra, monkeypatch):
     """UNSLOTH_RETURN_LOGITS=1 (models/llama.py:1525-1562: lm_head GEMM, caller-side shift, packed

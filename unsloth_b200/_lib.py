@@ -77,7 +77,6 @@ _SIGS = {
     "cdequantize_blockwise_bf16_nf4": ([_p, _p, _p, _p, _i, _i, _p], None),
     "cdequantize_blockwise_fp16_nf4": ([_p, _p, _p, _p, _i, _i, _p], None),
     "ub200_gemv_nf4": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _f, _i, _p], c_int),
-    "ub200_gemv_nf4_mma": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _f, _i, _p], c_int),
     "ub200_gemv_dense": ([_p, _p, _l, _p, _i, _i, _i, _i, _p], c_int),
     "cgemm_4bit_inference_naive_bf16": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], None),
     "cgemm_4bit_inference_naive_fp16": ([_i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], None),

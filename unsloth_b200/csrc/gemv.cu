@@ -51,7 +51,8 @@ template <> struct P2<__half> {
 // 14336 x 4096 weight (1.1-1.3 TB/s): ~6 issued instructions per weight (shift, mask, LDS, FFMA,
 // x unpack) at the power-capped ~1.4 GHz SM clock is an ISSUE bound of ~14 us plus a 2.02-wave
 // tail, not a DRAM bound.  Reaching the HBM roofline needs <= 2 instructions per weight, i.e. a
-// 16-bit pair table feeding HFMA2 / mma fragments -- round-2 work.
+// 16-bit pair table feeding HFMA2 (an `mma.sync` fragment variant was built and measured in round 2:
+// not faster, profiles/r2_gemv_bench.log, removed) -- DESIGN.md section 8.
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_nf4_lite_kernel(
     const T* __restrict__ x, const uint8_t* __restrict__ packed,
@@ -114,170 +115,6 @@ __global__ void __launch_bounds__(256) gemv_nf4_lite_kernel(
       v = fmaf(s, d, v);
     }
     out[row] = P2<T>::down(v);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (round-2 candidate; written after the round-1 GPU budget was spent: compiles for
-// sm_100a, NOT yet run on hardware, not on any product path -- reachable only through
-// ub200_gemv_nf4_mma).  The round-1 finding is that a table lookup + FFMA per weight costs ~6
-// issued instructions per weight, an issue bound 3x above the DRAM time.  Here a byte (two
-// weights) is looked up ONCE as a packed 16-bit pair and fed straight into the A fragment of
-// mma.sync.m16n8k16 (fp32 accumulate; the B fragment carries x, identical in all 8 columns), so
-// the multiply-adds cost one instruction per 256 weights and the total is ~2 instructions per
-// weight.  k order inside a 64-column block is permuted per lane (lane%4 = c owns columns
-// 16c..16c+15), which a dot product does not care about as long as x is permuted alike.
-// CTA = 32 rows x all of k: 8 warps interleave the 64-column steps (split-k), partial sums meet in
-// shared memory.  Per-block scale: the 4 mma of a step accumulate into a scratch fragment that is
-// scaled by the row's absmax once per 64 columns.
-// ---------------------------------------------------------------------------------------------
-template <typename T> struct MmaOp;
-template <> struct MmaOp<__nv_bfloat16> {
-  __device__ static __forceinline__ void run(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
-                                             uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-        "{%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-  }
-  __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-};
-template <> struct MmaOp<__half> {
-  __device__ static __forceinline__ void run(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
-                                             uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-        "{%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-  }
-  __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-};
-
-template <typename T>
-__global__ void __launch_bounds__(256) gemv_nf4_mma_kernel(
-    const T* __restrict__ x, const uint8_t* __restrict__ packed,
-    const float* __restrict__ absmax_f32, const uint8_t* __restrict__ absmax_q,
-    const float* __restrict__ code2, const float* __restrict__ absmax2,
-    const float* __restrict__ offset, const float* __restrict__ code16, T* __restrict__ out, int m,
-    int k, int bs_shift, int bs2_shift, const T* __restrict__ lora_B, int ldb,
-    const float* __restrict__ lora_t, int r, float s) {
-  // byte -> (code[hi nibble], code[lo nibble]) as a 16-bit pair, replicated per lane: 32 KB,
-  // every lookup of a warp is one conflict-free wavefront
-  __shared__ uint32_t lut[256 * 32];
-  __shared__ float red[8][32];
-  for (int e = threadIdx.x; e < 256 * 32; e += 256) {
-    const int b = e >> 5;
-    lut[e] = MmaOp<T>::pack(code16 ? code16[b >> 4] : kNF4g[b >> 4],
-                            code16 ? code16[b & 15] : kNF4g[b & 15]);
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, c = lane & 3;
-  const int row_base = blockIdx.x * 32;
-  const float off = offset ? *offset : 0.f;
-  const int64_t row_bytes = (int64_t)k / 2;
-  const uint32_t lane_bits = (uint32_t)lane << 2;
-  const char* lut_bytes = reinterpret_cast<const char*>(lut);
-  // rows of this lane: [rg][h] = row_base + rg*16 + g + 8h (clamped; results of clamped rows are dropped)
-  const uint8_t* wrow[2][2];
-#pragma unroll
-  for (int rg = 0; rg < 2; ++rg)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int row = row_base + rg * 16 + g + 8 * h;
-      row = row < m ? row : m - 1;
-      wrow[rg][h] = packed + row * row_bytes + c * 8;
-    }
-  // block scales: the 4 lanes of a group share their 4 rows; lane c rebuilds the scale of row
-  // #c (= rg*2 + h) and the group exchanges them by shuffle -- one dependent load chain per lane
-  // and step instead of four
-  int my_row = row_base + (c >> 1) * 16 + g + 8 * (c & 1);
-  my_row = my_row < m ? my_row : m - 1;
-  const int64_t my_blk0 = ((int64_t)my_row * k) >> bs_shift;       // k % blocksize == 0 (checked by the host)
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  const int n_steps = k >> 6;
-  uint2 wq[2][2], wn[2][2];
-  float am_mine, an_mine;
-  auto fetch = [&](int step, uint2 (&w)[2][2], float& a_mine) {
-#pragma unroll
-    for (int rg = 0; rg < 2; ++rg)
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        w[rg][h] = __ldcs(reinterpret_cast<const uint2*>(wrow[rg][h] + step * 32));
-    const int64_t blk = my_blk0 + ((step << 6) >> bs_shift);
-    a_mine = absmax_f32 ? absmax_f32[blk] : fmaf(code2[absmax_q[blk]], absmax2[blk >> bs2_shift], off);
-  };
-  int step = warp;                                  // the 8 warps interleave the 64-column steps
-  if (step < n_steps) fetch(step, wq, am_mine);
-#pragma unroll 1
-  for (; step < n_steps; step += 8) {
-    const bool more = step + 8 < n_steps;
-    if (more) fetch(step + 8, wn, an_mine);
-    float am[2][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) am[i >> 1][i & 1] = __shfl_sync(0xffffffffu, am_mine, (lane & ~3) | i);
-    // B fragment source: this lane's 16 columns of x (8 packed pairs), the same for every g
-    union { int4 v[2]; uint32_t p[8]; } xv;
-    const int4* xp = reinterpret_cast<const int4*>(x + (step << 6) + c * 16);
-    xv.v[0] = __ldg(xp);
-    xv.v[1] = __ldg(xp + 1);
-#pragma unroll
-    for (int rg = 0; rg < 2; ++rg) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t w0[2] = {wq[rg][0].x, wq[rg][0].y}, w1[2] = {wq[rg][1].x, wq[rg][1].y};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        // bytes 2t and 2t+1 of the 8-byte chunk: word t/2, byte positions 2(t&1), 2(t&1)+1
-        const int sh0 = 16 * (t & 1) - 7, sh1 = sh0 + 8;
-        const uint32_t u0 = w0[t >> 1], u1 = w1[t >> 1];
-        const uint32_t o00 = ((sh0 < 0 ? u0 << 7 : u0 >> sh0) & 0x7F80u) | lane_bits;   // row g,   byte 2t
-        const uint32_t o10 = ((sh0 < 0 ? u1 << 7 : u1 >> sh0) & 0x7F80u) | lane_bits;   // row g+8, byte 2t
-        const uint32_t o01 = ((u0 >> sh1) & 0x7F80u) | lane_bits;                        // row g,   byte 2t+1
-        const uint32_t o11 = ((u1 >> sh1) & 0x7F80u) | lane_bits;                        // row g+8, byte 2t+1
-        MmaOp<T>::run(d, *reinterpret_cast<const uint32_t*>(lut_bytes + o00),
-                      *reinterpret_cast<const uint32_t*>(lut_bytes + o10),
-                      *reinterpret_cast<const uint32_t*>(lut_bytes + o01),
-                      *reinterpret_cast<const uint32_t*>(lut_bytes + o11), xv.p[2 * t], xv.p[2 * t + 1]);
-      }
-      acc[rg][0] = fmaf(am[rg][0], d[0], acc[rg][0]);      // d[0], d[1]: row g   (all 8 columns equal)
-      acc[rg][1] = fmaf(am[rg][1], d[2], acc[rg][1]);      // d[2], d[3]: row g+8
-    }
-    if (more) {
-#pragma unroll
-      for (int rg = 0; rg < 2; ++rg)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) wq[rg][h] = wn[rg][h];
-      am_mine = an_mine;
-    }
-  }
-  if (c == 0) {
-#pragma unroll
-    for (int rg = 0; rg < 2; ++rg)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) red[warp][rg * 16 + g + 8 * h] = acc[rg][h];
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int row = row_base + threadIdx.x;
-    if (row < m) {
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-      if (lora_B) {
-        float dsum = 0.f;
-        for (int j = 0; j < r; ++j) dsum = fmaf(DT<T>::to_f(lora_B[(int64_t)row * ldb + j]), lora_t[j], dsum);
-        v = fmaf(s, dsum, v);
-      }
-      out[row] = P2<T>::down(v);
-    }
   }
 }
 
@@ -365,41 +202,6 @@ extern "C" int ub200_gemv_nf4(const void* x, const uint8_t* packed, const float*
                                  out, m, k, blocksize, blocksize2, lora_B, ldb, lora_t, r, s, stream);
 }
 
-// EXPERIMENTAL entry (see gemv_nf4_mma_kernel): same contract as ub200_gemv_nf4, k % 64 == 0 and
-// blocksize >= 64.  Not used by unsloth_b200.kernels; benchmarks/kernel_bench.py gemv_mma times it.
-extern "C" int ub200_gemv_nf4_mma(const void* x, const uint8_t* packed, const float* absmax_f32,
-                                  const uint8_t* absmax_q, const float* code2, const float* absmax2,
-                                  const float* offset, const float* code16, void* out, int m, int k,
-                                  int blocksize, int blocksize2, const void* lora_B, int ldb,
-                                  const float* lora_t, int r, float s, int dtype,
-                                  cudaStream_t stream) {
-  using namespace ub;
-  if (m <= 0) return UB200_OK;
-  if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_UNSUPPORTED;
-  if (k <= 0 || k % 64 || blocksize < 64 || (blocksize & (blocksize - 1)) || k % blocksize)
-    return UB200_ERR_UNSUPPORTED;
-  if (!absmax_f32 && (!absmax_q || !code2 || !absmax2 || blocksize2 <= 0)) return UB200_ERR_BAD_ARG;
-  if (!absmax_f32 && (blocksize2 & (blocksize2 - 1))) return UB200_ERR_UNSUPPORTED;
-  if (lora_B && (!lora_t || r <= 0 || ldb < r)) return UB200_ERR_BAD_ARG;
-  if (!x || !packed || !out || !al16(x) || !al16(packed)) return UB200_ERR_BAD_ARG;
-  int bs_shift = 0, bs2_shift = 0;
-  while ((1 << bs_shift) < blocksize) ++bs_shift;
-  while ((1 << bs2_shift) < blocksize2) ++bs2_shift;
-  const int grid = (m + 31) / 32;
-  if (dtype == UB200_BF16)
-    gemv_nf4_mma_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-        (const __nv_bfloat16*)x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16,
-        (__nv_bfloat16*)out, m, k, bs_shift, bs2_shift, (const __nv_bfloat16*)lora_B, ldb, lora_t, r, s);
-  else
-    gemv_nf4_mma_kernel<__half><<<grid, 256, 0, stream>>>(
-        (const __half*)x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16, (__half*)out,
-        m, k, bs_shift, bs2_shift, (const __half*)lora_B, ldb, lora_t, r, s);
-  UB_RETURN_LAST();
-}
-
-// bitsandbytes symbols (unsloth/kernels/utils.py:283-284, call at :955-973): A = x[k],
-// B = packed weight [m, k/2], absmax already fp32, datatype = the 16-entry code, n == 1.
-// `void` return like the original: argument errors are dropped, CUDA errors surface at next sync.
 extern "C" void cgemm_4bit_inference_naive_bf16(int m, int n, int k, __nv_bfloat16* A,
                                                 unsigned char* B, float* absmax, float* datatype,
                                                 __nv_bfloat16* out, int lda, int ldb, int ldc,

@@ -77,7 +77,7 @@ def fast_dequantize(W, quant_state=None, out=None, use_global_buffer=False, _slo
 # ---------------------------------------------------------------------------------------------
 # decode-time GEMV
 # ---------------------------------------------------------------------------------------------
-def _gemv_nf4(x, W, quant_state, out, lora_B=None, lora_t=None, s=0.0, _entry="ub200_gemv_nf4"):
+def _gemv_nf4(x, W, quant_state, out, lora_B=None, lora_t=None, s=0.0):
     absmax, shape, dtype, blocksize, offset, absmax2, code2, blocksize2 = _unpack_quant_state(quant_state)
     code16 = quant_state.code if type(quant_state) is not list else quant_state[6]
     if not torch.is_tensor(offset):
@@ -87,7 +87,7 @@ def _gemv_nf4(x, W, quant_state, out, lora_B=None, lora_t=None, s=0.0, _entry="u
     if x.dtype != dtype or out.dtype != dtype:
         raise RuntimeError("unsloth_b200: fast_gemv needs X and out in quant_state.dtype")
     r = 0 if lora_B is None else lora_B.shape[1]
-    L.call(_entry, L.ptr(x), L.ptr(W), None, L.ptr(absmax), L.ptr(code2), L.ptr(absmax2),
+    L.call("ub200_gemv_nf4", L.ptr(x), L.ptr(W), None, L.ptr(absmax), L.ptr(code2), L.ptr(absmax2),
            L.ptr(offset), None if code16 is None else L.ptr(code16), L.ptr(out), int(shape[0]),
            int(shape[1]), int(blocksize), int(blocksize2),
            None if lora_B is None else L.ptr(lora_B), 0 if lora_B is None else lora_B.stride(0),
