@@ -56,5 +56,36 @@ hid = torch.randn(1, 40, 512, device=DEV, dtype=BF, requires_grad=True)
 Wlm = (torch.randn(3000, 512, device=DEV) * 0.05).to(BF)
 K.unsloth_fused_ce_loss(None, hid * 1.0, Wlm, None, torch.randint(0, 3000, (1, 40), device=DEV), None, None, None,
                         chunk_rows=128).backward()
+# ---- round 2: grouped launches (in-kernel dependencies, split-K last-arriver reduction), LoRA_QKV / LoRA_MLP through
+# every schedule, fused-dequant GEMM, attention forward / backward (window, softcap, packed rows, D = 64 / 128 / 256)
+from unsloth_b200.kernels.utils import gemm_nf4  # noqa: E402
+for mode in (("1", "1"), ("1", "2"), ("0", "0")):
+    os.environ["UB200_GROUPED"] = "1" if mode[0] == "1" else "0"
+    os.environ["UB200_GROUPED_FWD"], os.environ["UB200_GROUPED_BWD"] = mode
+    def mk(o, i):
+        p_, q_ = quantize_nf4((torch.randn(o, i, device=DEV) * 0.02).to(BF))
+        return p_, q_, torch.nn.Parameter((torch.rand(16, i, device=DEV) - 0.5) / 8), torch.nn.Parameter(torch.randn(o, 16, device=DEV) * 0.05)
+    qp, kp, vp = mk(512, 512), mk(128, 512), mk(128, 512)
+    x = torch.randn(2, 150, 512, device=DEV, dtype=BF, requires_grad=True)
+    Qo, Ko, Vo = K.LoRA_QKV.apply(x * 1, qp[0], qp[1], qp[2], qp[3], 1.0, kp[0], kp[1], kp[2], kp[3], 1.0,
+                                  vp[0], vp[1], vp[2], vp[3], 1.0, True)
+    torch.autograd.backward([Qo, Ko, Vo], [torch.randn_like(Qo), torch.randn_like(Ko), torch.randn_like(Vo)])
+    gt, up, dn = mk(1408, 512), mk(1408, 512), mk(512, 1408)
+    o = K.LoRA_MLP.apply(x * 1, gt[0], gt[1], gt[2], gt[3], 1.0, up[0], up[1], up[2], up[3], 1.0, dn[0], dn[1], dn[2], dn[3], 1.0,
+                         K.swiglu_fg_kernel, K.swiglu_DWf_DW_dfg_kernel, True)
+    o.backward(torch.randn_like(o))
+for k_ in ("UB200_GROUPED", "UB200_GROUPED_FWD", "UB200_GROUPED_BWD"):
+    os.environ.pop(k_, None)
+Xn = torch.randn(300, 512, device=DEV, dtype=BF)
+gemm_nf4(Xn, p, qs, torch.empty(300, 320, device=DEV, dtype=BF))
+for (Bq, Sq, Hq, Hk, Dh, wl, cap, lengths) in [(2, 200, 4, 2, 128, -1, 0.0, None), (1, 333, 4, 2, 64, 100, 0.0, None),
+                                               (1, 260, 2, 1, 256, 64, 30.0, None), (1, 300, 4, 2, 128, -1, 0.0, [130, 170])]:
+    qa, ka, va = (torch.randn(Bq, Sq, h_, Dh, device=DEV, dtype=BF, requires_grad=True) for h_ in (Hq, Hk, Hk))
+    si = None
+    if lengths:
+        cu = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int32, device=DEV)
+        si = (torch.tensor(lengths, dtype=torch.int32, device=DEV), cu, max(lengths))
+    Oa = K.fast_attention(qa, ka, va, Dh ** -0.5, (wl, wl), cap, si)
+    Oa.backward(torch.randn_like(Oa))
 torch.cuda.synchronize()
 print("sanitize smoke ok")

@@ -8,7 +8,13 @@
 // Algorithmic bytes per element: fwd 3*b (e,g -> h), bwd 6*b (DW,e,g -> h,df,de in place).
 // Rounding points mirror the reference (f rounded to the tensor dtype before *g, all
 // products rounded to the tensor dtype; de evaluated in fp32) -- SURVEY.md section 9.
+#include <cstdlib>
+
 #include "common.cuh"
+
+#ifndef UB200_GLU_DEFAULT_VARIANT
+#define UB200_GLU_DEFAULT_VARIANT 1
+#endif
 
 namespace ub {
 
@@ -44,8 +50,8 @@ __device__ __forceinline__ void act_eval(float e, float& f, float& dfde) {
 // iteration left ~64 KB per SM outstanding, just under what 6.6 TB/s x ~1 us needs, and ran at
 // 0.88 of the measured copy bandwidth where the reference's Triton kernel (114,688 one-shot CTAs)
 // reached 1.0 (profiles/r2_ref_triton_ops.log).
-template <typename T, int ACT, int U>
-__global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ e,
+template <typename T, int ACT, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) glu_fwd_kernel(const T* __restrict__ e,
                                                       const T* __restrict__ g,
                                                       T* __restrict__ h, int64_t n_vec) {
   constexpr int V = DT<T>::VEC;
@@ -78,8 +84,8 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ e,
   }
 }
 
-template <typename T, int ACT, int U>
-__global__ void __launch_bounds__(256) glu_bwd_kernel(T* DW, T* e, T* g, int64_t n_vec) {
+template <typename T, int ACT, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) glu_bwd_kernel(T* DW, T* e, T* g, int64_t n_vec) {
   constexpr int V = DT<T>::VEC;
   const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n_vec; base += step) {
@@ -119,9 +125,16 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(T* DW, T* e, T* g, int64_t
   }
 }
 
+// UB200_GLU_VARIANT (numerics-neutral tuning probe): 0 = 4 (fwd) / 2 (bwd) vectors per thread in flight at the
+// compiler's register count, 1 = 2 / 1 vectors with the register count capped for full occupancy
+static int glu_variant() {
+  static const int v = [] { const char* e = getenv("UB200_GLU_VARIANT"); return e ? atoi(e) : UB200_GLU_DEFAULT_VARIANT; }();
+  return v;
+}
+
 static inline int ew_grid(int64_t n_vec, int threads) {
   int64_t b = (n_vec + threads - 1) / threads;
-  int64_t cap = (int64_t)UB_SM_COUNT * 16;
+  int64_t cap = (int64_t)UB_SM_COUNT * 32;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
@@ -134,8 +147,14 @@ extern "C" int ub200_glu_fwd(int act, const void* e, const void* g, void* h, int
   const int V = dtype == UB200_F32 ? 4 : 8;
   if (n % V) return UB200_ERR_BAD_ARG;
   const int64_t nv = n / V;
-  const int grid = ew_grid(nv, 256 * 4);
-#define GO(T, A) glu_fwd_kernel<T, A, 4><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv)
+  const int var = glu_variant();
+  const int grid = ew_grid(nv, 256 * (var == 1 ? 2 : (var == 2 ? 1 : 4)));
+#define GO(T, A)                                                                                          \
+  do {                                                                                                    \
+    if (var == 1) glu_fwd_kernel<T, A, 2, 6><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv); \
+    else if (var == 2) glu_fwd_kernel<T, A, 1, 8><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv); \
+    else glu_fwd_kernel<T, A, 4, 4><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv);         \
+  } while (0)
 #define GOA(T)                                                  \
   if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
   else if (act == ACT_GEGLU_APPROX) GO(T, ACT_GEGLU_APPROX);    \
@@ -157,8 +176,14 @@ extern "C" int ub200_glu_bwd(int act, void* DW, void* e, void* g, int64_t n, int
   const int V = dtype == UB200_F32 ? 4 : 8;
   if (n % V) return UB200_ERR_BAD_ARG;
   const int64_t nv = n / V;
-  const int grid = ew_grid(nv, 256 * 2);
-#define GO(T, A) glu_bwd_kernel<T, A, 2><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv)
+  const int var = glu_variant();
+  const int grid = ew_grid(nv, 256 * (var == 0 ? 2 : 1));
+#define GO(T, A)                                                                              \
+  do {                                                                                        \
+    if (var == 1) glu_bwd_kernel<T, A, 1, 5><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv); \
+    else if (var == 2) glu_bwd_kernel<T, A, 1, 4><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv); \
+    else glu_bwd_kernel<T, A, 2, 3><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv);         \
+  } while (0)
 #define GOA(T)                                                  \
   if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
   else if (act == ACT_GEGLU_APPROX) GO(T, ACT_GEGLU_APPROX);    \
