@@ -99,7 +99,7 @@ struct FwdCfg {
   static constexpr uint32_t KV_BYTES = (uint32_t)DB * BN * 128;      // one K (or V) tile
   static constexpr uint32_t P_BYTES = (uint32_t)(BN / 64) * BM * 128;
   static constexpr int STAGES = 2;
-  static constexpr uint32_t SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + 128 + 2048;   // P double-buffered
+  static constexpr uint32_t SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + 256 + 2048;   // P double-buffered
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static constexpr uint32_t TMEM_S0 = 0;                             // S buffers: 2 x BN columns
   static constexpr uint32_t TMEM_O = 2 * BN;                         // O: D columns
@@ -120,18 +120,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
   const uint32_t p_smem = kv_smem + C::STAGES * 2 * C::KV_BYTES;
   uint8_t* p_gen = smem_gen + (p_smem - smem_base);
   const uint32_t bar_base = p_smem + 2 * C::P_BYTES;
-  // barriers: q_full, k_full[2], v_full[2], kv_empty[2], s_full[2], p_full[2], p_empty[2], o_full
+  // barriers: q_full, k_full[2], v_full[2], v_empty[2], s_full[2], p_full[2], p_empty[2], o_full, k_empty[2]
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (3 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (5 + s); };
+  auto k_empty = [&](int s) { return bar_base + 8u * (14 + s); };   // K is released right after QK (not after PV)
   auto s_full = [&](int s) { return bar_base + 8u * (7 + s); };
   auto p_full = [&](int s) { return bar_base + 8u * (9 + s); };
   auto p_empty = [&](int s) { return bar_base + 8u * (11 + s); };
   const uint32_t o_full = bar_base + 8u * 13;
-  const uint32_t tmem_ptr_smem = bar_base + 8u * 14;
+  const uint32_t tmem_ptr_smem = bar_base + 8u * 16;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
-  const uint32_t xch_smem = bar_base + 128u;                        // 2 x 2 x 128 floats (row max / sum exchange)  [15 barriers + tmem ptr < 128 B]
+  const uint32_t xch_smem = bar_base + 256u;                        // 2 x 2 x 128 floats (row max / sum exchange)  [15 barriers + tmem ptr < 128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(s_full(s), 1);
+        mbar_init(k_full(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); mbar_init(k_empty(s), 1); mbar_init(s_full(s), 1);
       }
       for (int s = 0; s < 2; ++s) { mbar_init(p_full(s), 8); mbar_init(p_empty(s), 1); }   // one arrival per softmax warp
       mbar_init(o_full, 1);
@@ -188,21 +189,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
         tma_load_2d(q_smem + b * (BM * 128), &p.tmap_q, q_full, head * D + b * 64, seq_start + m0);
     }
     __syncwarp();
-    for (int t = 0; t < n_tiles; ++t) {
+    // K is released right after its score MMA and prefetched ONE tile further ahead than V: the score MMA
+    // of tile t+1 must never wait for a load that could only start after PV of tile t-1 (that chain
+    // serialised MMA and softmax in the first version: 26 % tensor-pipe activity)
+    auto load_k = [&](int t) {
       const int st = t & 1;
-      const uint32_t ph = (uint32_t)((t >> 1) & 1);
-      mbar_wait(kv_empty(st), ph ^ 1u);
-      const int n0 = (j_begin + t) * BN;
-      const uint32_t ks = kv_smem + st * 2 * C::KV_BYTES, vs = ks + C::KV_BYTES;
+      mbar_wait(k_empty(st), (uint32_t)(((t >> 1) & 1) ^ 1));
+      const uint32_t ks = kv_smem + st * 2 * C::KV_BYTES;
       if (elect_one()) {
         mbar_expect_tx(k_full(st), C::KV_BYTES);
 #pragma unroll
         for (int b = 0; b < C::DB; ++b)
-          tma_load_2d(ks + b * (BN * 128), &p.tmap_k, k_full(st), kv_head * D + b * 64, seq_start + n0);
+          tma_load_2d(ks + b * (BN * 128), &p.tmap_k, k_full(st), kv_head * D + b * 64, seq_start + (j_begin + t) * BN);
+      }
+      __syncwarp();
+    };
+    if (n_tiles > 0) load_k(0);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int st = t & 1;
+      if (t + 1 < n_tiles) load_k(t + 1);
+      mbar_wait(v_empty(st), (uint32_t)(((t >> 1) & 1) ^ 1));
+      const uint32_t vs = kv_smem + st * 2 * C::KV_BYTES + C::KV_BYTES;
+      if (elect_one()) {
         mbar_expect_tx(v_full(st), C::KV_BYTES);
 #pragma unroll
         for (int b = 0; b < C::DB; ++b)
-          tma_load_2d(vs + b * (BN * 128), &p.tmap_v, v_full(st), kv_head * D + b * 64, seq_start + n0);
+          tma_load_2d(vs + b * (BN * 128), &p.tmap_v, v_full(st), kv_head * D + b * 64, seq_start + (j_begin + t) * BN);
       }
       __syncwarp();
     }
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                      idesc_qk, (b > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(s_full(st));
+        umma_commit(k_empty(st));
       }
       __syncwarp();
     };
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
             umma_f16(tmem_base + C::TMEM_O, da + (uint64_t)(2 * k), db + (uint64_t)(128 * k), idesc_pv,
                      (t > 0 || kb > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(kv_empty(st));
+        umma_commit(v_empty(st));
         umma_commit(p_empty(st));
         if (t == n_tiles - 1) umma_commit(o_full);
       }
@@ -512,13 +525,16 @@ struct BwdCfg {
   static constexpr int NACC = MODE == BWD_DKV ? 2 : 1;               // accumulators
   static constexpr bool WANT_P = MODE == BWD_DKV || MODE == BWD_DV;
   static constexpr bool WANT_DS = MODE != BWD_DV;
-  // D = 256: two resident [128 x 256] operands already take 128 KB -> single-stage stream / tile
-  static constexpr int STAGES = (D == 256 && MODE != BWD_DV) ? 1 : 2;
+  // D = 256: two resident [128 x 256] operands already take 128 KB -> single-stage stream / tile.
+  // D <= 128: THREE stream stages -- a stage is only free once the accumulating MMAs of its unit have retired,
+  // so with two stages the load of unit u+1 could not start before compute(u-1) + acc(u-1) had finished and
+  // the score MMAs of u+1 (issued ahead of acc(u)) stalled the issuing thread on that load.
+  static constexpr int STAGES = D == 256 ? (MODE == BWD_DV ? 2 : 1) : 3;
   static constexpr int TBUF = D == 256 ? 1 : 2;
   static constexpr uint32_t OWN_BYTES = (uint32_t)DB * 128 * 128;    // one owner operand [128 x D]
   static constexpr uint32_t STR_BYTES = (uint32_t)DB * BU * 128;     // one streamed operand [64 x D]
   static constexpr uint32_t T_BYTES = 128 * 128;                     // one 16-bit [128 x 64] operand tile
-  static constexpr uint32_t SMEM_BYTES = NOWN * OWN_BYTES + STAGES * 2 * STR_BYTES + TBUF * NT * T_BYTES + 1024 + 256 + 2048;
+  static constexpr uint32_t SMEM_BYTES = NOWN * OWN_BYTES + STAGES * 2 * STR_BYTES + TBUF * NT * T_BYTES + 256 + 2048;
   static constexpr uint32_t TMEM_SC = 0;                             // score buffers: [2 units][2 kinds] x 64 columns
   static constexpr uint32_t TMEM_ACC = 256;                          // accumulators: NACC x D columns
   static constexpr uint32_t TMEM_COLS = 512;
@@ -530,9 +546,10 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = BwdCfg<D, MODE>;
   constexpr bool DKV = C::KEYS_OWN;               // owner rows are keys, per-column scalars come from the queries
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no room for an align-up pad: declared aligned, checked
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  uint8_t* smem_gen = smem_raw;
   const uint32_t own_smem = smem_base;                               // own1 | own2
   const uint32_t str_smem = own_smem + C::NOWN * C::OWN_BYTES;       // stage s: str1 | str2
   const uint32_t t_smem = str_smem + C::STAGES * 2 * C::STR_BYTES;   // buffer b: tile0 (| tile1)
@@ -540,13 +557,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
   const uint32_t bar_base = t_smem + C::TBUF * C::NT * C::T_BYTES;
   // barriers: own_full, str_full[2], str_empty[2], sc_full[2], t_full[2], t_empty[2], out_full
   const uint32_t own_full = bar_base;
-  auto str_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto str_empty = [&](int s) { return bar_base + 8u * (3 + s); };
-  auto sc_full = [&](int s) { return bar_base + 8u * (5 + s); };
-  auto t_full = [&](int s) { return bar_base + 8u * (7 + s); };
-  auto t_empty = [&](int s) { return bar_base + 8u * (9 + s); };
-  const uint32_t out_full = bar_base + 8u * 11;
-  const uint32_t tmem_ptr_smem = bar_base + 8u * 12;
+  auto str_full = [&](int s) { return bar_base + 8u * (1 + s); };     // up to 3 stages
+  auto str_empty = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto sc_full = [&](int s) { return bar_base + 8u * (7 + s); };
+  auto t_full = [&](int s) { return bar_base + 8u * (9 + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (11 + s); };
+  const uint32_t out_full = bar_base + 8u * 13;
+  const uint32_t tmem_ptr_smem = bar_base + 8u * 14;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
   float* vec = reinterpret_cast<float*>(smem_gen + (bar_base + 128u - smem_base));   // [2 buffers][2][64] lse2, delta
 
@@ -593,8 +610,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(own_full, 1);
+      for (int s = 0; s < 3; ++s) { mbar_init(str_full(s), 1); mbar_init(str_empty(s), 1); }
       for (int s = 0; s < 2; ++s) {
-        mbar_init(str_full(s), 1); mbar_init(str_empty(s), 1); mbar_init(sc_full(s), 1);
+        mbar_init(sc_full(s), 1);
         mbar_init(t_full(s), 8); mbar_init(t_empty(s), 1);        // one arrival per compute warp
       }
       mbar_init(out_full, 1);
@@ -668,7 +686,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
     if (n_units > 0) issue_scores(0);
     for (int u = 0; u < n_units; ++u) {
       const int st = u % C::STAGES, tbi = u % C::TBUF;
-      if (C::STAGES == 2 && u + 1 < n_units) issue_scores(u + 1);     // next unit's scores ahead of this unit's accumulation
+      if (C::STAGES >= 2 && u + 1 < n_units) issue_scores(u + 1);     // next unit's scores ahead of this unit's accumulation
       mbar_wait(t_full(tbi), (uint32_t)((u / C::TBUF) & 1));
       tc_fence_after();
       const uint32_t s1 = str_smem + st * 2 * C::STR_BYTES, s2 = s1 + C::STR_BYTES;
