@@ -28,6 +28,8 @@
 //
 // Roofline: tensor-bound in flops (4*S^2*D*Hq*B/2 causal) but in practice bounded by the MUFU
 // exp2 rate (16 / clk / SM: 1024 clk per 128x128 tile against 1024 clk of MMA for D = 128).
+#include <cstdlib>
+
 #include "tcgen05.cuh"
 
 namespace ub {
@@ -92,23 +94,27 @@ __device__ __forceinline__ uint32_t swz_off(int row, int col) {
   return (uint32_t)row * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)col & 7u) << 1);
 }
 
-template <int D, int BN>
+template <int D, int BN, int PBUF>
 struct FwdCfg {
   static constexpr int DB = D / 64;                                  // 64-wide column blocks of a row
   static constexpr uint32_t Q_BYTES = (uint32_t)DB * BM * 128;
   static constexpr uint32_t KV_BYTES = (uint32_t)DB * BN * 128;      // one K (or V) tile
   static constexpr uint32_t P_BYTES = (uint32_t)(BN / 64) * BM * 128;
   static constexpr int STAGES = 2;
-  static constexpr uint32_t SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + 256 + 2048;   // P double-buffered
+  // D <= 128 (S = 2048: 16 query tiles of 8.5 key tiles on average): 64-key tiles + ONE P buffer = 112.6 KB and 256
+  // TMEM columns, so TWO CTAs share an SM and the prologue / epilogue / hand-off latencies of one hide behind
+  // the MMAs and exps of the other.  D = 256: one CTA per SM, P double-buffered.
+  static constexpr uint32_t XCH_BYTES = 512;                         // row-max exchange: 2 halves x 128 rows x bf16
+  static constexpr uint32_t SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + PBUF * P_BYTES + 136 + XCH_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static constexpr uint32_t TMEM_S0 = 0;                             // S buffers: 2 x BN columns
   static constexpr uint32_t TMEM_O = 2 * BN;                         // O: D columns
   static constexpr uint32_t TMEM_COLS = (2 * BN + D) <= 256 ? 256 : 512;
 };
 
-template <int D, int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_constant__ FwdParams p) {
-  using C = FwdCfg<D, BN>;
+template <int D, int BN, int PBUF, int MINB>
+__global__ void __launch_bounds__(NUM_THREADS, MINB) attn_fwd_kernel(const __grid_constant__ FwdParams p) {
+  using C = FwdCfg<D, BN, PBUF>;
   // the swizzled tiles need 1024-byte alignment; the budget has no room for an align-up pad
   // (224 KB of tiles), so the dynamic segment is declared aligned and checked
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
   const uint32_t kv_smem = q_smem + C::Q_BYTES;                      // stage s: K at +s*2*KV, V at +KV
   const uint32_t p_smem = kv_smem + C::STAGES * 2 * C::KV_BYTES;
   uint8_t* p_gen = smem_gen + (p_smem - smem_base);
-  const uint32_t bar_base = p_smem + 2 * C::P_BYTES;
+  const uint32_t bar_base = p_smem + PBUF * C::P_BYTES;
   // barriers: q_full, k_full[2], v_full[2], v_empty[2], s_full[2], p_full[2], p_empty[2], o_full, k_empty[2]
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
   const uint32_t o_full = bar_base + 8u * 13;
   const uint32_t tmem_ptr_smem = bar_base + 8u * 16;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
-  const uint32_t xch_smem = bar_base + 256u;                        // 2 x 2 x 128 floats (row max / sum exchange)  [15 barriers + tmem ptr < 128 B]
+  const uint32_t xch_smem = bar_base + 136u;                        // 2 halves x 128 rows x bf16 (row-max exchange); 16 barriers + tmem ptr = 132 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -248,14 +254,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
     for (int t = 0; t < n_tiles; ++t) {
       const int st = t & 1;
       if (t + 1 < n_tiles) issue_qk(t + 1);
-      mbar_wait(p_full(st), (uint32_t)((t >> 1) & 1));
+      const int pb = t % PBUF;
+      mbar_wait(p_full(pb), (uint32_t)((t / PBUF) & 1));
       mbar_wait(v_full(st), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t vs = kv_smem + st * 2 * C::KV_BYTES + C::KV_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < BN / 64; ++kb) {
-          const uint64_t da = make_smem_desc(p_smem + st * C::P_BYTES + kb * (BM * 128), 16u, 1024u);
+          const uint64_t da = make_smem_desc(p_smem + pb * C::P_BYTES + kb * (BM * 128), 16u, 1024u);
           const uint64_t db = make_smem_desc(vs + kb * 8192u, (uint32_t)(BN * 128), 1024u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                      (t > 0 || kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(v_empty(st));
-        umma_commit(p_empty(st));
+        umma_commit(p_empty(pb));
         if (t == n_tiles - 1) umma_commit(o_full);
       }
       __syncwarp();
@@ -281,12 +288,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
     const int r = qd * 32 + lane;                 // query row of this thread inside the tile
     const int i_row = m0 + r;                     // position inside the sequence
     const uint32_t lane_addr = ((uint32_t)(qd * 32) << 16);
-    float* xch = reinterpret_cast<float*>(smem_gen + (xch_smem - smem_base));   // [2 buffers][2 halves][128 rows]
+    uint16_t* xch = reinterpret_cast<uint16_t*>(smem_gen + (xch_smem - smem_base));   // [2 halves][128 rows] bf16
     float m_used = -INFINITY;                     // max the stored P / O are relative to (log2 domain)
     float l = 0.f;
     const bool capped = p.softcap > 0.f;
     for (int t = 0; t < n_tiles; ++t) {
-      const int st = t & 1;
+      const int st = t & 1, pb = t % PBUF;
       const int n0 = (j_begin + t) * BN;
       mbar_wait(s_full(st), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
@@ -320,10 +327,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
       for (int i = 0; i < HC; ++i) mx = fmaxf(mx, sv[i]);
       if (!capped) mx *= p.scale_log2;                          // scale > 0: max commutes with it
       // ---- row maximum over both halves -----------------------------------------------------------
-      float* xb = xch + (t & 1) * 256;
-      xb[ch * 128 + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-      mx = fmaxf(mx, xb[(ch ^ 1) * 128 + r]);
+      // both partners use the bf16-rounded (upwards) values, so they agree on the reference maximum bit for bit
+      {
+        const __nv_bfloat16 own = __float2bfloat16_ru(mx);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");          // partner has read the previous tile's value
+        xch[ch * 128 + r] = __bfloat16_as_ushort(own);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+        mx = fmaxf(__bfloat162float(own), __bfloat162float(__ushort_as_bfloat16(xch[(ch ^ 1) * 128 + r])));
+      }
       const float m_new = fmaxf(m_used, mx);
       // lazy rescale: advance the reference maximum only when it grew by more than 2^TAU (P stays
       // <= 2^TAU, harmless in fp32 / bf16), so O is rarely touched.  tcgen05.ld/st are warp-wide
@@ -346,11 +357,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
         if (p.is_fp16) { __half2 h = __floats2half2_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
         else { __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
       }
-      // this P buffer's previous user (the PV MMA of tile t-2) must have retired
-      mbar_wait(p_empty(st), (uint32_t)(((t >> 1) & 1) ^ 1));
+      // this P buffer's previous user (the PV MMA of tile t - PBUF) must have retired
+      mbar_wait(p_empty(pb), (uint32_t)(((t / PBUF) & 1) ^ 1));
       if (__any_sync(0xffffffffu, touch_o)) {
-        // O is rescaled between PV(t-1) and PV(t): wait for PV(t-1) (the other buffer's last commit)
-        mbar_wait(p_empty(st ^ 1), (uint32_t)((((t - 1) >> 1) & 1)));
+        // O is rescaled between PV(t-1) and PV(t): wait for PV(t-1)
+        mbar_wait(p_empty((t - 1) % PBUF), (uint32_t)(((t - 1) / PBUF) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < HD; c0 += 32) {
@@ -367,22 +378,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
 #pragma unroll
       for (int g = 0; g < HC / 8; ++g) {
         const int col = cb + g * 8;                              // column inside the tile
-        *reinterpret_cast<uint4*>(p_gen + st * C::P_BYTES + (col >> 6) * (BM * 128) + swz_off(r, col & 63)) =
+        *reinterpret_cast<uint4*>(p_gen + pb * C::P_BYTES + (col >> 6) * (BM * 128) + swz_off(r, col & 63)) =
             make_uint4(pw[4 * g], pw[4 * g + 1], pw[4 * g + 2], pw[4 * g + 3]);
       }
       fence_proxy_async_smem();                   // generic-proxy smem writes -> tensor-core reads
       tc_fence_before();
       __syncwarp();                               // 256 arrivals on one mbarrier serialise: one per warp
-      if (lane == 0) mbar_arrive(p_full(st));
+      if (lane == 0) mbar_arrive(p_full(pb));
     }
     // ---- epilogue: O / l -> 16-bit rows, LSE ---------------------------------------------------
+    if (n_tiles > 0) { mbar_wait(o_full, 0); tc_fence_after(); }
     {
-      float* xb = xch + (n_tiles & 1) * 256;      // the buffer the last tile did NOT use
+      // the two halves of a row add their partial sums through the (now idle) P region
+      float* xb = reinterpret_cast<float*>(p_gen);
       xb[ch * 128 + r] = l;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
       l += xb[(ch ^ 1) * 128 + r];
     }
-    if (n_tiles > 0) { mbar_wait(o_full, 0); tc_fence_after(); }
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const bool row_ok = i_row < seq_len;
     uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + (int64_t)(seq_start + i_row) * p.ldo + (int64_t)head * D + ch * HD;
@@ -431,17 +443,17 @@ static int make_tmap_rows(CUtensorMap* map, const void* ptr, int64_t rows, int64
   return make_tmap(map, ptr, rows, cols, ld, box_rows, fp16);
 }
 
-template <int D, int BN>
+template <int D, int BN, int PBUF, int MINB>
 static int launch_fwd(const FwdParams& p, dim3 grid, cudaStream_t st) {
-  using C = FwdCfg<D, BN>;
+  using C = FwdCfg<D, BN, PBUF>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D, BN, PBUF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  attn_fwd_kernel<D, BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  attn_fwd_kernel<D, BN, PBUF, MINB><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
   return UB200_OK;
 }
 
@@ -979,7 +991,8 @@ extern "C" int ub200_attention_fwd(const void* Q, const void* K, const void* V, 
   FwdParams p;
   memset(&p, 0, sizeof(p));
   const int fp16 = dtype == UB200_F16;
-  const int BN = head_dim == 256 ? 64 : 128;
+  const int fwd_mode = [] { const char* e = getenv("UB200_ATTN_FWD"); return e ? atoi(e) : 2; }();   // 1: 128-key tiles, 1 CTA/SM; 2: 64-key tiles, 2 CTAs/SM
+  const int BN = (head_dim == 256 || fwd_mode == 2) ? 64 : 128;
   int rc;
   if ((rc = make_tmap_rows(&p.tmap_q, Q, tokens, (int64_t)n_heads_q * head_dim, q_row_stride, BM, fp16))) return rc;
   if ((rc = make_tmap_rows(&p.tmap_k, K, tokens, (int64_t)n_heads_k * head_dim, k_row_stride, BN, fp16))) return rc;
@@ -994,9 +1007,9 @@ extern "C" int ub200_attention_fwd(const void* Q, const void* K, const void* V, 
   p.is_fp16 = fp16;
   const int longest = cu_seqlens ? max_seqlen : seqlen;
   dim3 grid((longest + BM - 1) / BM, n_heads_q, cu_seqlens ? n_docs : batch);
-  if (head_dim == 64) rc = launch_fwd<64, 128>(p, grid, stream);
-  else if (head_dim == 128) rc = launch_fwd<128, 128>(p, grid, stream);
-  else rc = launch_fwd<256, 64>(p, grid, stream);
+  if (head_dim == 256) rc = launch_fwd<256, 64, 2, 1>(p, grid, stream);
+  else if (fwd_mode == 2) rc = head_dim == 64 ? launch_fwd<64, 64, 1, 2>(p, grid, stream) : launch_fwd<128, 64, 1, 2>(p, grid, stream);
+  else rc = head_dim == 64 ? launch_fwd<64, 128, 2, 1>(p, grid, stream) : launch_fwd<128, 128, 2, 1>(p, grid, stream);
   if (rc) return rc;
   UB_RETURN_LAST();
 }
