@@ -405,15 +405,18 @@ def fast_dequantize(W, quant_state=None):
     return out.t() if W.shape[0] == 1 else out
 
 
-def gemv_nf4(x, packed, qs):
+def gemv_nf4(x, packed, qs, code_dtype=None):
     """`fast_gemv`, kernels/utils.py:874-973 (bsz == q_len == 1): fp32 absmax (:938-948), then
     bitsandbytes' 4-bit GEMV out[m] = sum_k NF4[nibble(m,k)] * absmax[(m*K+k)//bs] * x[k], rounded
     once to quant_state.dtype.  bitsandbytes is absent (parity unpinned): this is the exact-product
-    fp32 form; the original multiplies in the 16-bit dtype before accumulating in fp32."""
+    fp32 form; the original casts the 16-entry code table (and absmax, and every product) to the
+    16-bit dtype before accumulating in fp32.  `code_dtype` = that dtype restates the first of those
+    roundings only -- the arithmetic of csrc/gemv.cu's pair-table kernel."""
     absmax = dequantize_absmax(qs)
     b = packed.reshape(-1).long()
     idx = torch.stack([b >> 4, b & 0xF], dim=1).reshape(-1)
-    Wf = (NF4_CODE[idx] * absmax[torch.arange(idx.numel()) // qs.blocksize]).reshape(qs.shape)
+    code = NF4_CODE if code_dtype is None else NF4_CODE.to(code_dtype).float()
+    Wf = (code[idx] * absmax[torch.arange(idx.numel()) // qs.blocksize]).reshape(qs.shape)
     return (Wf.double() @ x.reshape(-1).double()).float().to(qs.dtype)
 
 

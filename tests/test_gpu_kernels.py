@@ -329,7 +329,9 @@ def test_nf4_dequant_bit_exact_and_bnb_symbols():
 
 
 @pytest.mark.parametrize("m,k,dt", [(4096, 4096, torch.bfloat16), (14336, 4096, torch.bfloat16),
-                                    (1000, 1024, torch.float16), (4096, 14336, torch.bfloat16)])
+                                    (1000, 1024, torch.float16), (4096, 14336, torch.bfloat16),
+                                    (264, 1088, torch.bfloat16), (40, 96, torch.float16),
+                                    (1000, 11008, torch.bfloat16), (50, 1152, torch.float16)])
 def test_fast_gemv_nf4_vs_oracle_and_bnb_symbol(m, k, dt):
     """Decode-time GEMV on the packed weight: against the oracle's exact-product
     restatement, against dequantise-then-matmul on the GPU, and through the bitsandbytes symbol
@@ -346,11 +348,18 @@ def test_fast_gemv_nf4_vs_oracle_and_bnb_symbol(m, k, dt):
     from types import SimpleNamespace as NS
     qs_cpu = NS(absmax=qs.absmax.cpu(), shape=qs.shape, dtype=dt, blocksize=64, offset=qs.offset.cpu(),
                 state2=NS(absmax=qs.state2.absmax.cpu(), code=qs.state2.code.cpu(), blocksize=256))
-    ref = R.gemv_nf4(x.cpu(), packed.cpu(), qs_cpu)
-    # one rounding of an fp32 dot product on both sides: at most one ulp of the output dtype apart
+    # the kernel's arithmetic: code table in the 16-bit dtype (as bitsandbytes' GEMV holds it), exact products,
+    # fp32 absmax and accumulation, one rounding: at most one ulp of the output dtype from the restatement
+    # (shapes outside the pair-table kernel's domain -- k % 128, k < 1024 -- run the fp32-table kernel)
+    pair = k % 128 == 0 and k >= 1024
+    ref = R.gemv_nf4(x.cpu(), packed.cpu(), qs_cpu, code_dtype=dt if pair else None)
     o, rf = out.view(-1).float().cpu(), ref.float()
     assert (o - rf).abs().max() <= 8e-3 * rf.abs().max()
     assert ((o - rf).abs() > 1e-3 * rf.abs().max()).float().mean() < 0.02
+    # and against the fp32-table form (no rounding of the codes): the table rounding is worth < 1 output ulp
+    rf32 = R.gemv_nf4(x.cpu(), packed.cpu(), qs_cpu).float()
+    assert (o - rf32).abs().max() <= 1.2e-2 * rf32.abs().max()
+    assert (o - rf32).abs().mean() <= 1.5e-3 * rf32.abs().max()
     Wd = fast_dequantize(packed, qs)
     ref2 = (Wd.float() @ x.view(-1).float())
     assert (out.view(-1).float() - ref2).abs().max() <= 1.2e-2 * ref2.abs().max()

@@ -29,6 +29,7 @@
 // Roofline: tensor-bound in flops (4*S^2*D*Hq*B/2 causal) but in practice bounded by the MUFU
 // exp2 rate (16 / clk / SM: 1024 clk per 128x128 tile against 1024 clk of MMA for D = 128).
 #include <cstdlib>
+#include <type_traits>
 
 #include "tcgen05.cuh"
 
@@ -76,6 +77,31 @@ __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): the softmax warps are ISSUE-bound next to the MMAs (about four
+// instructions per score), one instruction per TWO scores for the scale-subtract and the row sum
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t r, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -290,7 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) attn_fwd_kernel(const __gri
     const uint32_t lane_addr = ((uint32_t)(qd * 32) << 16);
     uint16_t* xch = reinterpret_cast<uint16_t*>(smem_gen + (xch_smem - smem_base));   // [2 halves][128 rows] bf16
     float m_used = -INFINITY;                     // max the stored P / O are relative to (log2 domain)
-    float l = 0.f;
+    uint64_t l2 = pack2(0.f, 0.f);                // row sum, as two partial sums (even / odd columns)
     const bool capped = p.softcap > 0.f;
     for (int t = 0; t < n_tiles; ++t) {
       const int st = t & 1, pb = t % PBUF;
@@ -314,8 +340,13 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) attn_fwd_kernel(const __gri
       }
       // scores in the log2 domain: t = s * scale * log2(e)   (soft-capped: cap*log2(e) * tanh(s*scale/cap))
       if (capped) {
+        const uint64_t soc2 = pack2(p.scale_over_cap, p.scale_over_cap), cl2 = pack2(p.cap_log2, p.cap_log2);
 #pragma unroll
-        for (int i = 0; i < HC; ++i) sv[i] = p.cap_log2 * tanh_approx(sv[i] * p.scale_over_cap);
+        for (int i = 0; i < HC; i += 2) {
+          float a0, a1;
+          unpack2(fmul2(pack2(sv[i], sv[i + 1]), soc2), a0, a1);
+          unpack2(fmul2(pack2(tanh_approx(a0), tanh_approx(a1)), cl2), sv[i], sv[i + 1]);
+        }
       }
       if (need_mask) {
 #pragma unroll
@@ -343,20 +374,25 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) attn_fwd_kernel(const __gri
       const float m_next = want ? m_new : m_used;
       const float alpha = (m_used == -INFINITY) ? 1.0f : ex2f(m_used - m_next);
       const bool touch_o = t > 0 && want && m_used > -INFINITY;
-      l *= alpha;
+      l2 = fmul2(l2, pack2(alpha, alpha));
       m_used = m_next;
       const float m_sub = m_used == -INFINITY ? 0.f : m_used;
       // ---- P = exp2(t - m) -> 16-bit, kept in registers until the previous PV MMA has retired ----
       const float mul = capped ? 1.0f : p.scale_log2;
       uint32_t pw[HC / 2];
+      const uint64_t mul2 = pack2(mul, mul), nm2 = pack2(-m_sub, -m_sub);
+      auto exps = [&](auto fp16_tag) {
 #pragma unroll
-      for (int i = 0; i < HC; i += 2) {
-        const float e0 = ex2f(fmaf(sv[i], mul, -m_sub));         // exp2(-inf) = 0 for masked entries
-        const float e1 = ex2f(fmaf(sv[i + 1], mul, -m_sub));
-        l += e0 + e1;
-        if (p.is_fp16) { __half2 h = __floats2half2_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
-        else { __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
-      }
+        for (int i = 0; i < HC; i += 2) {
+          float a0, a1;
+          unpack2(ffma2(pack2(sv[i], sv[i + 1]), mul2, nm2), a0, a1);
+          const float e0 = ex2f(a0), e1 = ex2f(a1);              // exp2(-inf) = 0 for masked entries
+          l2 = fadd2(l2, pack2(e0, e1));
+          if constexpr (decltype(fp16_tag)::value) { __half2 h = __floats2half2_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
+          else { __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h); }
+        }
+      };
+      if (p.is_fp16) exps(std::true_type{}); else exps(std::false_type{});   // uniform branch: one F2FP per pair, not two predicated
       // this P buffer's previous user (the PV MMA of tile t - PBUF) must have retired
       mbar_wait(p_empty(pb), (uint32_t)(((t / PBUF) & 1) ^ 1));
       if (__any_sync(0xffffffffu, touch_o)) {
@@ -369,8 +405,13 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) attn_fwd_kernel(const __gri
           const uint32_t o_addr = tmem_base + lane_addr + C::TMEM_O + (uint32_t)(ch * HD + c0);
           tmem_ld32(o_addr, v);
           tmem_ld_wait(v);
+          const uint64_t al2 = pack2(alpha, alpha);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          for (int i = 0; i < 32; i += 2) {
+            float a0, a1;
+            unpack2(fmul2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), al2), a0, a1);
+            v[i] = __float_as_uint(a0); v[i + 1] = __float_as_uint(a1);
+          }
           tmem_st32(o_addr, v);
         }
         tmem_st_wait();
@@ -388,6 +429,8 @@ __global__ void __launch_bounds__(NUM_THREADS, MINB) attn_fwd_kernel(const __gri
     }
     // ---- epilogue: O / l -> 16-bit rows, LSE ---------------------------------------------------
     if (n_tiles > 0) { mbar_wait(o_full, 0); tc_fence_after(); }
+    float l;
+    { float la, lb; unpack2(l2, la, lb); l = la + lb; }
     {
       // the two halves of a row add their partial sums through the (now idle) P region
       float* xb = reinterpret_cast<float*>(p_gen);
