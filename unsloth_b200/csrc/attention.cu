@@ -791,8 +791,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
     // dQ: the per-row scalars are fixed for the whole kernel
     float row_lse2 = 0.f, row_delta = 0.f;
     if (!DKV && own_pos < seq_len) {
-      row_lse2 = p.lse[vec_index(own_head, own_pos)] * 1.4426950408889634f;
-      row_delta = p.delta[vec_index(own_head, own_pos)];
+      row_lse2 = p.lse[vec_index(own_head, own_pos)] * -1.4426950408889634f;       // -lse2
+      row_delta = p.delta[vec_index(own_head, own_pos)] * p.scale;                 // delta * scale
     }
     // dKV: per-column scalars of unit u live in vec[u & 1]; the loader threads (cw < 128) fetch the
     // next unit's while the current one is processed
@@ -802,12 +802,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
         const int c = cw & 63, pos = unit_row0(u) + c;
         const float* src = (cw < 64) ? p.lse : p.delta;
         pre = pos < seq_len ? src[vec_index(unit_head(u), pos)] : 0.f;
-        if (cw < 64) pre *= 1.4426950408889634f;
+        pre *= (cw < 64) ? -1.4426950408889634f : p.scale;     // stored as -lse2 | delta * scale (what the packed math adds)
       }
     };
     if (DKV) {
       prefetch_vec(0);
-      if (cw < 128) vec[cw] = pre;                // buffer 0: [lse2 64 | delta 64]
+      if (cw < 128) vec[cw] = pre;                // buffer 0: [-lse2 64 | delta*scale 64]
     }
     for (int u = 0; u < n_units; ++u) {
       const int st = u & 1;                       // score buffer / scalar buffer
@@ -833,39 +833,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_bwd_kernel(const __grid_c
                                     (u0 + BU > seq_len) || (o0 + 128 > seq_len));
       const float* vb = vec + st * 128;
       uint32_t pw[16], dw[16];
+      // P = exp2(t - lse2), dS = P * (dP - delta) * scale (* (1 - tanh^2) when soft-capped), two columns per
+      // instruction (FFMA2 / FMUL2); dtype and capping are uniform branches around the whole loop
+      const uint64_t sl2 = pack2(p.scale_log2, p.scale_log2), sc2 = pack2(p.scale, p.scale);
+      const uint64_t row_nl2 = pack2(row_lse2, row_lse2), row_nd2 = pack2(-row_delta, -row_delta);
+      auto elementwise = [&](auto fp16_tag, auto capped_tag) {
+        constexpr bool FP16 = decltype(fp16_tag)::value, CAPPED = decltype(capped_tag)::value;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float pv[2], dv[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = cb + i + e;
-          const float s = __uint_as_float(sraw[i + e]);
-          float th = 0.f, tt;
-          if (capped) { th = tanh_approx(s * p.scale_over_cap); tt = p.cap_log2 * th; }
-          else tt = s * p.scale_log2;
-          const float lse2 = DKV ? vb[c] : row_lse2;
-          const float dl = DKV ? vb[64 + c] : row_delta;
-          float pe = ex2f(tt - lse2);
+        for (int i = 0; i < 32; i += 2) {
+          const int c = cb + i;
+          const float s0 = __uint_as_float(sraw[i]), s1 = __uint_as_float(sraw[i + 1]);
+          uint64_t nl2 = row_nl2, nd2 = row_nd2;             // -lse2 | -(delta * scale) of the two columns
+          if (DKV) {
+            const float2 a = *reinterpret_cast<const float2*>(vb + c), b = *reinterpret_cast<const float2*>(vb + 64 + c);
+            nl2 = pack2(a.x, a.y); nd2 = pack2(-b.x, -b.y);
+          }
+          float th0 = 0.f, th1 = 0.f, t0, t1;
+          if (CAPPED) {
+            th0 = tanh_approx(s0 * p.scale_over_cap); th1 = tanh_approx(s1 * p.scale_over_cap);
+            unpack2(ffma2(pack2(th0, th1), pack2(p.cap_log2, p.cap_log2), nl2), t0, t1);
+          } else {
+            unpack2(ffma2(pack2(s0, s1), sl2, nl2), t0, t1);
+          }
+          float pe0 = ex2f(t0), pe1 = ex2f(t1);
           if (need_mask) {
-            const int qi = DKV ? u0 + c : own_pos, kj = DKV ? own_pos : u0 + c;
-            const bool vis = (kj <= qi) && (p.window < 0 || qi - kj <= p.window) && (qi < seq_len) && (kj < seq_len);
-            if (!vis) pe = 0.f;
+            const int q0 = DKV ? u0 + c : own_pos, k0 = DKV ? own_pos : u0 + c;
+            const int q1 = DKV ? q0 + 1 : q0, k1 = DKV ? k0 : k0 + 1;
+            const bool v0 = (k0 <= q0) && (p.window < 0 || q0 - k0 <= p.window) && (q0 < seq_len) && (k0 < seq_len);
+            const bool v1 = (k1 <= q1) && (p.window < 0 || q1 - k1 <= p.window) && (q1 < seq_len) && (k1 < seq_len);
+            if (!v0) pe0 = 0.f;
+            if (!v1) pe1 = 0.f;
           }
-          float ds = 0.f;
+          float d0 = 0.f, d1 = 0.f;
           if (C::WANT_DS) {
-            ds = pe * (__uint_as_float(draw[i + e]) - dl) * p.scale;
-            if (capped) ds *= (1.0f - th * th);
+            // (dP * scale - delta * scale) * P
+            uint64_t x2 = ffma2(pack2(__uint_as_float(draw[i]), __uint_as_float(draw[i + 1])), sc2, nd2);
+            x2 = fmul2(x2, pack2(pe0, pe1));
+            if (CAPPED) x2 = fmul2(x2, pack2(1.0f - th0 * th0, 1.0f - th1 * th1));
+            unpack2(x2, d0, d1);
           }
-          pv[e] = pe; dv[e] = ds;
+          if (FP16) {
+            __half2 h = __floats2half2_rn(pe0, pe1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            __half2 g = __floats2half2_rn(d0, d1); dw[i >> 1] = *reinterpret_cast<uint32_t*>(&g);
+          } else {
+            __nv_bfloat162 h = __floats2bfloat162_rn(pe0, pe1); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            __nv_bfloat162 g = __floats2bfloat162_rn(d0, d1); dw[i >> 1] = *reinterpret_cast<uint32_t*>(&g);
+          }
         }
-        if (p.is_fp16) {
-          __half2 h = __floats2half2_rn(pv[0], pv[1]); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-          __half2 g = __floats2half2_rn(dv[0], dv[1]); dw[i >> 1] = *reinterpret_cast<uint32_t*>(&g);
-        } else {
-          __nv_bfloat162 h = __floats2bfloat162_rn(pv[0], pv[1]); pw[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-          __nv_bfloat162 g = __floats2bfloat162_rn(dv[0], dv[1]); dw[i >> 1] = *reinterpret_cast<uint32_t*>(&g);
-        }
-      }
+      };
+      if (p.is_fp16) { if (capped) elementwise(std::true_type{}, std::true_type{}); else elementwise(std::true_type{}, std::false_type{}); }
+      else { if (capped) elementwise(std::false_type{}, std::true_type{}); else elementwise(std::false_type{}, std::false_type{}); }
       uint8_t* tb = t_gen + tbi * C::NT * C::T_BYTES;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
