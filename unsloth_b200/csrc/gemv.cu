@@ -10,13 +10,16 @@
 //  * ub200_gemv_dense: 16-bit dense rows (the `torch.mv(lm_head, h)` of models/llama.py:1460 and
 //    the `A x` LoRA temp).
 //
-// bitsandbytes is not vendored in the reference: the arithmetic here (fp32 code * fp32 absmax,
-// fp32 accumulation over k) restates the published NF4 layout and is at least as accurate as the
-// 16-bit products of the original; parity against bitsandbytes itself is unpinned.
+// bitsandbytes is not vendored in the reference: the arithmetic here restates the published NF4 layout.
+// Pair-table kernel (the default): code table rounded to the 16-bit dtype (as bitsandbytes' own GEMV holds
+// its quant_map), exact products (HMMA, fp32 accumulate), fp32 absmax applied to fp32 partial sums -- the
+// oracle's gemv_nf4(code_dtype=).  Lite kernel (shapes outside the pair kernel's domain): fp32 code * fp32
+// absmax, fp32 accumulation.  Both at least as accurate as the 16-bit products of the original; parity
+// against bitsandbytes itself is unpinned.
 //
 // HBM-bound by bytes.  Algorithmic bytes per call: m*k*(0.5 + 1/blocksize) + k*2 + m*2 (NF4);
-// m*k*2 + k*2 + m*out_bytes (dense).  One warp owns a row (NF4) or two rows (dense) and walks k
-// in 1024- / 256-column steps, 16 bytes per lane per step.
+// m*k*2 + k*2 + m*out_bytes (dense).  Measured (profiles/r2_gemv_bench.log, r2_gemv_ncu.txt): NF4 13.8 us for
+// 14336 x 4096 = 2.2 TB/s = 0.33 of the measured copy bandwidth (round 1: 27 us, 0.17); dense 0.94.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -46,16 +49,11 @@ template <> struct P2<__half> {
   __device__ static __forceinline__ __half down(float v) { return __float2half_rn(v); }
 };
 
-// One row per warp; the 16-entry fp32 code table is replicated per LANE in shared memory (2 KB:
-// entry n of lane l at n*32 + l), so every lookup of a warp is conflict-free and costs one
-// wavefront whatever the nibbles are; 40 registers per thread => 48 resident warps per SM.
-// Round-1 status (profiles/r1_gemv_nf4_ncu.txt, profiles/r1_kernel_bench_gemv_addrms.log): this
-// kernel and a 32 KB byte-pair-table variant with 4 rows per warp both land at 24-28 us for a
-// 14336 x 4096 weight (1.1-1.3 TB/s): ~6 issued instructions per weight (shift, mask, LDS, FFMA,
-// x unpack) at the power-capped ~1.4 GHz SM clock is an ISSUE bound of ~14 us plus a 2.02-wave
-// tail, not a DRAM bound.  Reaching the HBM roofline needs <= 2 instructions per weight, i.e. a
-// 16-bit pair table feeding HFMA2 (an `mma.sync` fragment variant was built and measured in round 2:
-// not faster, profiles/r2_gemv_bench.log, removed) -- DESIGN.md section 8.
+// Lite kernel (round 1; now the fallback for k % 128 != 0, k < 1024 or blocksize < 64): one row per warp; the
+// 16-entry fp32 code table is replicated per LANE in shared memory (2 KB: entry n of lane l at n*32 + l), so
+// every lookup of a warp is conflict-free and costs one wavefront whatever the nibbles are.  ~6 issued
+// instructions and ONE shared-memory lookup per weight: 24-28 us for a 14336 x 4096 weight (1.1-1.3 TB/s), an
+// issue / LSU bound, not a DRAM bound (profiles/r1_gemv_nf4_ncu.txt).
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_nf4_lite_kernel(
     const T* __restrict__ x, const uint8_t* __restrict__ packed,
@@ -171,7 +169,8 @@ template <> struct MmaOp<__half> {
 // warp's item (16 rows x 2 blocks) are fetched one per LANE, four stages ahead, and handed to the accumulating
 // lanes by shuffle.  Requires k % 128 == 0, k >= 1024, blocksize >= 64 (else the lite kernel).
 constexpr int GEMV_STAGES = 4;
-constexpr int GEMV_STAGE_BYTES = 16 * 512;
+constexpr int GEMV_ROW_STRIDE = 512 + 64;        // rows 64 B apart (mod 128): the two rows of an LDS.128 phase cover all 32 banks
+constexpr int GEMV_STAGE_BYTES = 16 * GEMV_ROW_STRIDE;
 constexpr int GEMV_SMEM = 32768 + GEMV_STAGES * GEMV_STAGE_BYTES + 1024 + 1024 + 64 + 64;
 
 template <typename T>
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
   constexpr int S = GEMV_STAGES;
   extern __shared__ __align__(128) uint8_t gsm[];
   uint32_t* lut = reinterpret_cast<uint32_t*>(gsm);                       // [256 byte values][32 lanes]
-  uint8_t* ring = gsm + 32768;                                            // [S][16 rows][512 B]
+  uint8_t* ring = gsm + 32768;                                            // [S][16 rows][512 B + 64 B pad]
   float* code2_s = reinterpret_cast<float*>(ring + S * GEMV_STAGE_BYTES); // [256]
   float* red = code2_s + 256;                                             // [2][8][16]
   uint16_t* c16 = reinterpret_cast<uint16_t*>(red + 256);                 // [16]
@@ -206,8 +205,10 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
     for (int i = 0; i < S; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 8); }
     fence_barrier_init();
   }
+  // global loads of the prologue are issued here and consumed as late as possible (the kernel is a few
+  // microseconds long: a DRAM round trip in front of the table build was 40 % of the warps' lifetime)
+  const float code2_mine = (code2 && threadIdx.x < 256) ? code2[threadIdx.x] : 0.f;
   if (threadIdx.x < 16) c16[threadIdx.x] = MmaOp<T>::bits(code16 ? code16[threadIdx.x] : kNF4g[threadIdx.x]);
-  if (threadIdx.x < 256) code2_s[threadIdx.x] = code2 ? code2[threadIdx.x] : 0.f;
   __syncthreads();
 
   if (warp == 8) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
       if (lane < 16) {
         const int row = min((grp << 4) + lane, m - 1);                    // clamped rows: computed, dropped
         const uint8_t* src = packed + (int64_t)row * half_k + off;
-        const uint32_t dst = smem_u32(ring) + slot * GEMV_STAGE_BYTES + lane * 512;
+        const uint32_t dst = smem_u32(ring) + slot * GEMV_STAGE_BYTES + lane * GEMV_ROW_STRIDE;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst), "l"(src), "r"(seg), "r"(full(slot)) : "memory");
       }
@@ -239,7 +240,6 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
 #pragma unroll
     for (int i = 0; i < 32; ++i) lut[(warp * 32 + i) * 32 + lane] = (i < 16 ? hi0 : hi1) | ((uint32_t)c16[i & 15] << 16);
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
   const int g = lane >> 2, t = lane & 3;
   const int bpr = k >> bs_shift;                       // absmax blocks per row
   const uint32_t lane_base = smem_u32(lut) + ((uint32_t)lane << 2);
@@ -249,13 +249,16 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
 
   // absmax prefetch: lane L owns (row L >> 1, block L & 1) of the warp's chunk; raw bits, S stages ahead
   int p_grp = blockIdx.x, p_sc = 0;
-  auto scale_fetch = [&]() -> uint32_t {
+  auto blk_of = [&](int grp, int sc) -> int {
+    const int row = min((grp << 4) + (lane >> 1), m - 1);
+    const int cb = min(((((sc << 3) + warp) << 7) + ((lane & 1) << 6)) >> bs_shift, bpr - 1);
+    return row * bpr + cb;
+  };
+  auto scale_fetch = [&]() -> uint32_t {              // the RAW loaded value: nothing depends on it until it is consumed
     uint32_t v = 0u;
     if (p_grp < n_groups) {
-      const int row = min((p_grp << 4) + (lane >> 1), m - 1);
-      const int cb = min(((((p_sc << 3) + warp) << 7) + ((lane & 1) << 6)) >> bs_shift, bpr - 1);
-      const int blk = row * bpr + cb;
-      v = absmax_f32 ? __float_as_uint(absmax_f32[blk]) : (uint32_t)absmax_q[blk] | ((uint32_t)(blk >> bs2_shift) << 8);
+      const int blk = blk_of(p_grp, p_sc);
+      v = absmax_f32 ? __float_as_uint(absmax_f32[blk]) : (uint32_t)absmax_q[blk];
       if (++p_sc == n_sc) { p_sc = 0; p_grp += gridDim.x; }
     }
     return v;
@@ -263,13 +266,15 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
   uint32_t sq[S];
 #pragma unroll
   for (int i = 0; i < S; ++i) sq[i] = scale_fetch();
+  if (threadIdx.x < 256) code2_s[threadIdx.x] = code2_mine;
+  asm volatile("bar.sync 1, 256;" ::: "memory");       // table + code2_s visible to the 8 consumer warps
 
   int c_grp = blockIdx.x, c_sc = 0, parity = 0;
   float acc0 = 0.f, acc1 = 0.f;
   uint32_t xb[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) xb[q] = 0u;             // stays zero in the lanes that feed no B column
-  const uint32_t ring_lane = smem_u32(ring) + g * 512 + warp * 64 + t * 16;
+  const uint32_t ring_lane = smem_u32(ring) + g * GEMV_ROW_STRIDE + warp * 64 + t * 16;
 
   auto step = [&](int j, uint32_t& sqv) {
     const int slot = j % S;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
       }
     }
     // absmax2 is a second (cached) global load: issued here, resolved only after the MMAs
-    const float a2 = absmax_f32 ? 0.f : absmax2[sqv >> 8];
+    const float a2 = absmax_f32 ? 0.f : absmax2[blk_of(c_grp, c_sc) >> bs2_shift];
     const uint32_t sq_now = sqv;
     sqv = scale_fetch();
     mbar_wait(full(slot), (uint32_t)((j / S) & 1));
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u0[0]), "=r"(u0[1]), "=r"(u0[2]), "=r"(u0[3])
                  : "r"(ring_lane + slot * GEMV_STAGE_BYTES));
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u1[0]), "=r"(u1[1]), "=r"(u1[2]), "=r"(u1[3])
-                 : "r"(ring_lane + slot * GEMV_STAGE_BYTES + 8 * 512));
+                 : "r"(ring_lane + slot * GEMV_STAGE_BYTES + 8 * GEMV_ROW_STRIDE));
     __syncwarp();
     if (lane == 0) mbar_arrive(empty(slot));           // the slot is free once every warp holds its bytes in registers
     float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulation chains
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
       if (i & 1) MmaOp<T>::mma(e, a, xb[2 * i], xb[2 * i + 1]);
       else MmaOp<T>::mma(d, a, xb[2 * i], xb[2 * i + 1]);
     }
-    const float mine = absmax_f32 ? __uint_as_float(sq_now) : fmaf(code2_s[sq_now & 0xFFu], a2, off);
+    const float mine = absmax_f32 ? __uint_as_float(sq_now) : fmaf(code2_s[sq_now], a2, off);
     const float sc0 = __shfl_sync(0xffffffffu, mine, src0), sc1 = __shfl_sync(0xffffffffu, mine, src1);
     // D columns 2t, 2t+1 = segments 2t, 2t+1 = ONE absmax block (>= 64 columns); columns >= 4 are zero
     acc0 = fmaf(sc0, (d[0] + d[1]) + (e[0] + e[1]), acc0);

@@ -77,6 +77,12 @@ def fast_dequantize(W, quant_state=None, out=None, use_global_buffer=False, _slo
 # ---------------------------------------------------------------------------------------------
 # decode-time GEMV
 # ---------------------------------------------------------------------------------------------
+_NF4_CODE = torch.tensor([-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453,
+                          -0.28444138169288635, -0.18477343022823334, -0.09105003625154495, 0.0,
+                          0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,
+                          0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0], dtype=torch.float32)
+
+
 def _gemv_nf4(x, W, quant_state, out, lora_B=None, lora_t=None, s=0.0):
     absmax, shape, dtype, blocksize, offset, absmax2, code2, blocksize2 = _unpack_quant_state(quant_state)
     code16 = quant_state.code if type(quant_state) is not list else quant_state[6]
@@ -84,6 +90,18 @@ def _gemv_nf4(x, W, quant_state, out, lora_B=None, lora_t=None, s=0.0):
         offset = torch.tensor(float(offset), dtype=torch.float32, device=W.device)
     if code16 is not None and (code16.dtype != torch.float32 or code16.numel() != 16):
         raise RuntimeError("unsloth_b200: fast_gemv needs the 16-entry fp32 NF4 code")
+    if code16 is not None and type(quant_state) is not list:
+        # the standard NF4 table is a constant inside the kernel: passing no pointer takes one global
+        # round trip out of the prologue of a ~10 us launch.  Checked once per quant_state (one D2H).
+        std = getattr(quant_state, "_ub_std_nf4", None)
+        if std is None or std[0] != code16.data_ptr():
+            std = (code16.data_ptr(), bool(torch.equal(code16.detach().float().cpu(), _NF4_CODE)))
+            try:
+                quant_state._ub_std_nf4 = std
+            except AttributeError:
+                pass
+        if std[1]:
+            code16 = None
     if x.dtype != dtype or out.dtype != dtype:
         raise RuntimeError("unsloth_b200: fast_gemv needs X and out in quant_state.dtype")
     r = 0 if lora_B is None else lora_B.shape[1]
