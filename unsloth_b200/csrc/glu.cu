@@ -13,7 +13,7 @@
 #include "common.cuh"
 
 #ifndef UB200_GLU_DEFAULT_VARIANT
-#define UB200_GLU_DEFAULT_VARIANT 1
+#define UB200_GLU_DEFAULT_VARIANT 4
 #endif
 
 namespace ub {
@@ -45,25 +45,27 @@ __device__ __forceinline__ void act_eval(float e, float& f, float& dfde) {
   }
 }
 
-// Each thread keeps U independent 16-byte vectors of every operand in flight per iteration (the
-// loads of a batch are all issued before the first use): a grid-stride loop with ONE vector per
-// iteration left ~64 KB per SM outstanding, just under what 6.6 TB/s x ~1 us needs, and ran at
-// 0.88 of the measured copy bandwidth where the reference's Triton kernel (114,688 one-shot CTAs)
-// reached 1.0 (profiles/r2_ref_triton_ops.log).
-template <typename T, int ACT, int U, int MINB>
-__global__ void __launch_bounds__(256, MINB) glu_fwd_kernel(const T* __restrict__ e,
-                                                      const T* __restrict__ g,
-                                                      T* __restrict__ h, int64_t n_vec) {
+// Launch shape (measured, profiles/r2_glu_variants.log): the default is ONE-SHOT CTAs of 128 threads, one
+// 16-byte vector of every operand per thread -- the grid covers the tensor (114,688 CTAs at cfg2) and the
+// hardware block scheduler balances the tail; that is the shape of the reference's Triton launch and reaches
+// the same 6.7 TB/s on the backward (0.211 ms, forward 0.115 ms = 6.1 TB/s).  The grid-stride form (variant 1:
+// U vectors per thread per iteration, 32 CTAs per SM) ran 7 % behind: 6.05 rounds of the stride leave a 7th,
+// 5 %-full round that one CTA in twenty pays for in full.
+template <typename T, int ACT, int U, int MINB, int BS = 256, bool ONE = false, bool CS = true, bool STCS = false>
+__global__ void __launch_bounds__(BS, MINB) glu_fwd_kernel(const T* __restrict__ e,
+                                                     const T* __restrict__ g,
+                                                     T* __restrict__ h, int64_t n_vec) {
   constexpr int V = DT<T>::VEC;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  // ONE: one-shot CTAs (the grid covers the tensor, the hardware block scheduler balances the tail)
+  const int64_t step = ONE ? n_vec : (int64_t)gridDim.x * blockDim.x * U;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n_vec; base += step) {
     int4 er[U], gr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = base + (int64_t)u * blockDim.x;
       if (i < n_vec) {
-        er[u] = __ldcs(reinterpret_cast<const int4*>(e + i * V));
-        gr[u] = __ldcs(reinterpret_cast<const int4*>(g + i * V));
+        er[u] = CS ? __ldcs(reinterpret_cast<const int4*>(e + i * V)) : __ldg(reinterpret_cast<const int4*>(e + i * V));
+        gr[u] = CS ? __ldcs(reinterpret_cast<const int4*>(g + i * V)) : __ldg(reinterpret_cast<const int4*>(g + i * V));
       }
     }
 #pragma unroll
@@ -79,24 +81,24 @@ __global__ void __launch_bounds__(256, MINB) glu_fwd_kernel(const T* __restrict_
         act_eval<ACT, sizeof(T) == 2>(DT<T>::to_f(ev[k]), f, d);
         o[k] = DT<T>::rnd(f) * DT<T>::to_f(gv[k]);
       }
-      store_vec<T>(h + i * V, o);
+      if (STCS) store_vec_cs<T>(h + i * V, o); else store_vec<T>(h + i * V, o);
     }
   }
 }
 
-template <typename T, int ACT, int U, int MINB>
-__global__ void __launch_bounds__(256, MINB) glu_bwd_kernel(T* DW, T* e, T* g, int64_t n_vec) {
+template <typename T, int ACT, int U, int MINB, int BS = 256, bool ONE = false, bool CS = true>
+__global__ void __launch_bounds__(BS, MINB) glu_bwd_kernel(T* DW, T* e, T* g, int64_t n_vec) {
   constexpr int V = DT<T>::VEC;
-  const int64_t step = (int64_t)gridDim.x * blockDim.x * U;
+  const int64_t step = ONE ? n_vec : (int64_t)gridDim.x * blockDim.x * U;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n_vec; base += step) {
     int4 dr[U], er[U], gr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = base + (int64_t)u * blockDim.x;
       if (i < n_vec) {
-        dr[u] = __ldcs(reinterpret_cast<const int4*>(DW + i * V));
-        er[u] = __ldcs(reinterpret_cast<const int4*>(e + i * V));
-        gr[u] = __ldcs(reinterpret_cast<const int4*>(g + i * V));
+        dr[u] = CS ? __ldcs(reinterpret_cast<const int4*>(DW + i * V)) : *reinterpret_cast<const int4*>(DW + i * V);
+        er[u] = CS ? __ldcs(reinterpret_cast<const int4*>(e + i * V)) : *reinterpret_cast<const int4*>(e + i * V);
+        gr[u] = CS ? __ldcs(reinterpret_cast<const int4*>(g + i * V)) : *reinterpret_cast<const int4*>(g + i * V);
       }
     }
 #pragma unroll
@@ -125,8 +127,8 @@ __global__ void __launch_bounds__(256, MINB) glu_bwd_kernel(T* DW, T* e, T* g, i
   }
 }
 
-// UB200_GLU_VARIANT (numerics-neutral tuning probe): 0 = 4 (fwd) / 2 (bwd) vectors per thread in flight at the
-// compiler's register count, 1 = 2 / 1 vectors with the register count capped for full occupancy
+// UB200_GLU_VARIANT (numerics-neutral tuning probe): 4 (default) = one-shot CTAs, 1 = grid-stride, 7 = one-shot
+// with streaming stores on the forward
 static int glu_variant() {
   static const int v = [] { const char* e = getenv("UB200_GLU_VARIANT"); return e ? atoi(e) : UB200_GLU_DEFAULT_VARIANT; }();
   return v;
@@ -148,12 +150,13 @@ extern "C" int ub200_glu_fwd(int act, const void* e, const void* g, void* h, int
   if (n % V) return UB200_ERR_BAD_ARG;
   const int64_t nv = n / V;
   const int var = glu_variant();
-  const int grid = ew_grid(nv, 256 * (var == 1 ? 2 : (var == 2 ? 1 : 4)));
-#define GO(T, A)                                                                                          \
-  do {                                                                                                    \
-    if (var == 1) glu_fwd_kernel<T, A, 2, 6><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv); \
-    else if (var == 2) glu_fwd_kernel<T, A, 1, 8><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv); \
-    else glu_fwd_kernel<T, A, 4, 4><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv);         \
+  const int grid = ew_grid(nv, 256 * 2);
+  const unsigned one = (unsigned)((nv + 127) / 128);
+#define GO(T, A)                                                                                                            \
+  do {                                                                                                                      \
+    if (var == 1) glu_fwd_kernel<T, A, 2, 6><<<grid, 256, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv);                  \
+    else if (var == 7) glu_fwd_kernel<T, A, 1, 16, 128, true, true, true><<<one, 128, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv); \
+    else glu_fwd_kernel<T, A, 1, 16, 128, true><<<one, 128, 0, stream>>>((const T*)e, (const T*)g, (T*)h, nv);                 \
   } while (0)
 #define GOA(T)                                                  \
   if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
@@ -177,12 +180,12 @@ extern "C" int ub200_glu_bwd(int act, void* DW, void* e, void* g, int64_t n, int
   if (n % V) return UB200_ERR_BAD_ARG;
   const int64_t nv = n / V;
   const int var = glu_variant();
-  const int grid = ew_grid(nv, 256 * (var == 0 ? 2 : 1));
-#define GO(T, A)                                                                              \
-  do {                                                                                        \
-    if (var == 1) glu_bwd_kernel<T, A, 1, 5><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv); \
-    else if (var == 2) glu_bwd_kernel<T, A, 1, 4><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv); \
-    else glu_bwd_kernel<T, A, 2, 3><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv);         \
+  const int grid = ew_grid(nv, 256);
+  const unsigned one = (unsigned)((nv + 127) / 128);
+#define GO(T, A)                                                                                           \
+  do {                                                                                                     \
+    if (var == 1) glu_bwd_kernel<T, A, 1, 5><<<grid, 256, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv);            \
+    else glu_bwd_kernel<T, A, 1, 10, 128, true><<<one, 128, 0, stream>>>((T*)DW, (T*)e, (T*)g, nv);          \
   } while (0)
 #define GOA(T)                                                  \
   if (act == ACT_SWIGLU) GO(T, ACT_SWIGLU);                     \
