@@ -275,9 +275,12 @@ def run_ours(args):
     dev_ids, dev_lab = host_ids.to(dev), host_lab.to(dev)
 
     def eager_step(ids, lab):
-        bucket.zero_grad()
-        out = model(input_ids=ids, labels=lab)
-        out.loss.backward()
+        bucket.begin_step()                 # zero_grad + batched LoRA cast refresh
+        try:
+            out = model(input_ids=ids, labels=lab)
+            out.loss.backward()
+        finally:
+            bucket.end_backward()           # batched accumulation of the LoRA gradients
         bucket.all_reduce_grads()
         bucket.step()
         return out.loss

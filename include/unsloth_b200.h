@@ -290,6 +290,30 @@ int ub200_cast_pad_2d(const void* src, int src_dtype, int64_t src_ld, int rows, 
                       int dst_row_off, int dst_col_off, float scale, int transpose,
                       cudaStream_t stream);
 
+/* Batched forms of the two per-adapter housekeeping steps of a LoRA training step (448 tensors each on
+ * Llama-3-8B): descriptors are a HOST array, forwarded by value in the kernel parameters (chunks of 40 per
+ * launch), so the calls are CUDA-graph capturable and need no device staging.
+ *  ub200_cast_pad_multi : every element = ub200_cast_pad_2d of one descriptor (the per-step A.to(dtype) /
+ *                         (s*B).to(dtype) refresh of unsloth/kernels/utils.py:1163-1167, fast_lora.py:138-153)
+ *  ub200_accumulate_multi: dst[r, c] (contiguous fp32 [rows, cols]) += src[r*src_rs + c*src_cs] -- what
+ *                         autograd's AccumulateGrad does for the d_A / d_B views the reference's backward
+ *                         returns (fast_lora.py:206-229, 519-540, 639-650), as one launch per 40 adapters.      */
+typedef struct {
+  const void* src; void* dst;
+  int64_t src_ld, dst_ld;
+  int src_dtype, dst_dtype;
+  int rows, cols, dst_rows, dst_cols, row_off, col_off;
+  float scale;
+  int transpose;
+} ub200_cast_desc;
+typedef struct {
+  const float* src; float* dst;
+  int64_t src_rs, src_cs;
+  int rows, cols;
+} ub200_acc_desc;
+int ub200_cast_pad_multi(const ub200_cast_desc* descs, int n, cudaStream_t stream);
+int ub200_accumulate_multi(const ub200_acc_desc* descs, int n, cudaStream_t stream);
+
 /* Flat AdamW over the LoRA parameter bucket (fp32 p, g, m, v of length n), decoupled weight
  * decay; bias corrections are passed in (1 - beta^t).  grad_scale multiplies g first.          */
 int ub200_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr,

@@ -192,6 +192,22 @@ def cast_pad_2d(src, sdt, sld, rows, cols, dst, ddt, dld, drows, dcols, roff, co
     Dv[roff:roff + s.shape[0], coff:coff + s.shape[1]] = s.to(_DT[ddt])
 
 
+def cast_pad_multi(descs, n, stream):
+    for i in range(n):
+        d = descs[i]
+        cast_pad_2d(d.src, d.src_dtype, d.src_ld, d.rows, d.cols, d.dst, d.dst_dtype, d.dst_ld, d.dst_rows,
+                    d.dst_cols, d.row_off, d.col_off, d.scale, d.transpose, stream)
+
+
+def accumulate_multi(descs, n, stream):
+    for i in range(n):
+        d = descs[i]
+        span = (d.rows - 1) * d.src_rs + (d.cols - 1) * d.src_cs + 1
+        src = mem(d.src, torch.float32, span).as_strided((d.rows, d.cols), (d.src_rs, d.src_cs))
+        dst = view2d(d.dst, torch.float32, d.rows, d.cols, d.cols)
+        dst += src
+
+
 def gemv_nf4(x, packed, absmax_f32, absmax_q, code2, absmax2, offset, code16, out, m, k, bs, bs2, lora_B,
              ldb, lora_t, r, s, dt, stream):
     d = _DT[dt]
@@ -225,6 +241,7 @@ _TABLE = {
     "ub200_cross_entropy_fwd": cross_entropy_fwd, "ub200_cross_entropy_bwd": cross_entropy_bwd,
     "ub200_dequantize_nf4": dequantize_nf4, "ub200_quantize_nf4": quantize_nf4, "ub200_gemm": gemm, "ub200_gemm_grouped": gemm_grouped,
     "ub200_cast_pad_2d": cast_pad_2d, "ub200_gemv_nf4": gemv_nf4,
+    "ub200_cast_pad_multi": cast_pad_multi, "ub200_accumulate_multi": accumulate_multi,
     "ub200_gemv_dense": gemv_dense,
 }
 

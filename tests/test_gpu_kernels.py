@@ -500,3 +500,48 @@ def test_fp16_path_matches_oracle():
     K.gemm(200, 136, [(A, B, 256)], out)
     ref = A.float() @ B.float().t()
     assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 2e-3
+
+
+def test_cast_pad_multi_and_accumulate_multi_match_the_single_tensor_forms():
+    """ub200_cast_pad_multi / ub200_accumulate_multi (descriptors by value, chunks of 40 per launch): every
+    descriptor = ub200_cast_pad_2d / `dst += view`, bit for bit, over more than two chunks of mixed shapes,
+    offsets, scales, transposes and (for the accumulation) transposed / column-sliced source views."""
+    from unsloth_b200 import _lib as L
+    from unsloth_b200.kernels.utils import cast_pad
+    torch.manual_seed(5)
+    n = 97
+    srcs, dsts, refs, arr = [], [], [], (L.CastDesc * n)()
+    for i in range(n):
+        r, c = [(16, 4096), (8, 1024), (4096, 16), (33, 70), (1, 5)][i % 5]
+        tr = i % 3 == 1
+        dt = [torch.bfloat16, torch.float16, torch.float32][i % 3]
+        src = torch.randn(r, c, device=DEV)
+        pr, pc = (c, r) if tr else (r, c)
+        ro, co = (i % 2) * 3, (i % 4) * 5
+        dst = torch.full((pr + ro + 2, pc + co + 7), 7.0, dtype=dt, device=DEV)
+        ref = torch.full_like(dst, 7.0)
+        cast_pad(src, ref, ro, co, 0.5 + i, tr)
+        d = arr[i]
+        d.src, d.dst, d.src_ld, d.dst_ld = src.data_ptr(), dst.data_ptr(), src.stride(0), dst.stride(0)
+        d.src_dtype, d.dst_dtype, d.rows, d.cols = L.dt(src), L.dt(dst), r, c
+        d.dst_rows, d.dst_cols, d.row_off, d.col_off, d.scale, d.transpose = dst.shape[0], dst.shape[1], ro, co, 0.5 + i, int(tr)
+        srcs.append(src); dsts.append(dst); refs.append(ref)
+    L.call("ub200_cast_pad_multi", arr, n, L.stream())
+    for a, b in zip(dsts, refs):
+        assert torch.equal(a, b)
+    acc = (L.AccDesc * n)()
+    gs, views, exp = [], [], []
+    for i in range(n):
+        r, c = [(16, 4096), (4096, 16), (8, 1024), (5, 3)][i % 4]
+        full = torch.randn(c, 64, device=DEV) if i % 2 == 0 else torch.randn(r, 64, device=DEV)
+        view = full[:, 3:3 + r].t() if i % 2 == 0 else full[:, 7:7 + c]
+        if view.shape != (r, c):
+            full = torch.randn(r, max(c, 64) + 9, device=DEV); view = full[:, 7:7 + c]
+        g = torch.randn(r, c, device=DEV)
+        exp.append(g + view)
+        a = acc[i]
+        a.src, a.dst, a.src_rs, a.src_cs, a.rows, a.cols = view.data_ptr(), g.data_ptr(), view.stride(0), view.stride(1), r, c
+        gs.append(g); views.append((full, view))
+    L.call("ub200_accumulate_multi", acc, n, L.stream())
+    for g, e in zip(gs, exp):
+        assert torch.equal(g, e)

@@ -653,3 +653,54 @@ def test_kv_cache_decode_loop_matches_full_forward(cpu_model, name, extra):
                 logits = model._ub_final_softcap * torch.tanh(logits / model._ub_final_softcap)
             cur = torch.cat([cur, logits[:, -1].argmax(-1, keepdim=True)], 1)
     assert torch.equal(out, cur)
+
+
+@pytest.mark.parametrize("name,extra", [("llama-3-8b", {}), ("gemma-2-9b", {"query_pre_attn_scalar": 16, "sliding_window": 8})])
+def test_step_plan_batches_casts_and_gradient_accumulation(cpu_model, emu, name, extra):
+    """FlatLoRABucket.begin_step() / end_backward() (kernels/utils.py::StepPlan): from the second step on the
+    per-adapter cast launches collapse into ub200_cast_pad_multi and the d_A / d_B of every projection reach the
+    flat gradient bucket through ub200_accumulate_multi instead of autograd's AccumulateGrad -- with the SAME
+    losses and gradients as the plain autograd route, also after a raw in-place parameter update between steps."""
+    from unsloth_b200.ddp import FlatLoRABucket
+    from unsloth_b200.kernels import utils as KU
+    P = cpu_model
+    torch.manual_seed(11)
+    model = _build(P, name, **extra)
+    torch.manual_seed(11)
+    ref = _build(P, name, **extra)
+    ids = torch.randint(0, TINY["vocab_size"], (2, 16))
+    bucket = FlatLoRABucket(P.lora_parameters(model))
+    n_params = len(bucket.params)
+    for step in range(3):
+        # reference route: autograd accumulates each gradient on its own
+        _zero(P, ref)
+        lr_ = ref(input_ids=ids, labels=ids).loss
+        lr_.backward()
+        g_ref = _grads(P, ref)
+        del emu[:]
+        bucket.begin_step()
+        loss = model(input_ids=ids, labels=ids).loss
+        loss.backward()
+        bucket.end_backward()
+        assert KU.ACTIVE_PLAN is None and not bucket.plan.in_step
+        assert loss.item() == lr_.item()
+        g = torch.cat([p.grad.flatten() for p in P.lora_parameters(model)])
+        assert torch.equal(g, g_ref), (step, (g - g_ref).abs().max())
+        assert emu.count("ub200_accumulate_multi") == 1 and len(bucket.plan.grad_pairs) == 0
+        if step == 0:
+            assert "ub200_cast_pad_2d" in emu and "ub200_cast_pad_multi" not in emu       # the recording step
+            n_casts = sum(len(e[4]) for e in bucket.plan.entries.values())
+            assert n_casts >= n_params                              # every adapter tensor is cast at least once
+        else:
+            assert "ub200_cast_pad_2d" not in emu and emu.count("ub200_cast_pad_multi") == 1
+            assert sum(len(e[4]) for e in bucket.plan.entries.values()) == n_casts
+        # a raw in-place update on BOTH copies (no _version bump, no optimiser hook): the next step must see it
+        with torch.no_grad():
+            torch.manual_seed(100 + step)
+            for p, q in zip(P.lora_parameters(model), P.lora_parameters(ref)):
+                d = 0.05 * torch.randn_like(p)
+                p.data.add_(d); q.data.add_(d)
+    # outside a step nothing is taken from the plan: a plain forward rebuilds its casts
+    del emu[:]
+    model(input_ids=ids, labels=ids)
+    assert "ub200_cast_pad_2d" in emu and "ub200_cast_pad_multi" not in emu

@@ -43,6 +43,18 @@ class GemmProblem(Structure):
 GROUPED_MAX_PROBLEMS, GROUPED_MAX_SEGMENTS = 8, 4
 
 
+class CastDesc(Structure):          # ub200_cast_desc
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_ld", c_int64), ("dst_ld", c_int64),
+                ("src_dtype", c_int), ("dst_dtype", c_int), ("rows", c_int), ("cols", c_int),
+                ("dst_rows", c_int), ("dst_cols", c_int), ("row_off", c_int), ("col_off", c_int),
+                ("scale", c_float), ("transpose", c_int)]
+
+
+class AccDesc(Structure):           # ub200_acc_desc
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_rs", c_int64), ("src_cs", c_int64),
+                ("rows", c_int), ("cols", c_int)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         # build in-tree when a compiler is around (developer box); never fall back to CPU code
@@ -91,6 +103,8 @@ _SIGS = {
                              _f, _i, _f, _i, _p], c_int),
     "ub200_cast_pad_2d": ([_p, _i, _l, _i, _i, _p, _i, _l, _i, _i, _i, _i, _f, _i, _p], c_int),
     "ub200_adamw_flat": ([_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _f, _p], c_int),
+    "ub200_cast_pad_multi": ([POINTER(CastDesc), _i, _p], c_int),
+    "ub200_accumulate_multi": ([POINTER(AccDesc), _i, _p], c_int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 for _name, (_args, _res) in _SIGS.items():

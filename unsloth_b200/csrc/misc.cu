@@ -64,9 +64,86 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     upd(p[i], g[i], m[i], v[i]);
 }
 
+// ---- batched forms: one launch for MANY small tensors ------------------------------------------
+// A QLoRA step refreshes 448 LoRA casts and (with autograd) accumulates 448 LoRA gradients, each a
+// 4-5 us launch moving a few hundred KB: 1.8 % of the step as ~900 launches (profiles/
+// r2_launches_bench_full_summary.txt).  The descriptors travel BY VALUE in the kernel parameters
+// (a chunk of 40 per launch, < 4 KB), so nothing has to be staged on the device and the launches
+// are CUDA-graph capturable; blockIdx.y = descriptor, blockIdx.x strides over its elements.
+constexpr int MULTI_CHUNK = 40;
+constexpr int MULTI_CTAS = 8;
+struct CastBatch { ub200_cast_desc d[MULTI_CHUNK]; };
+struct AccBatch { ub200_acc_desc d[MULTI_CHUNK]; };
+
+__global__ void __launch_bounds__(256) cast_pad_multi_kernel(const __grid_constant__ CastBatch b) {
+  const ub200_cast_desc& d = b.d[blockIdx.y];
+  const int64_t total = (int64_t)d.dst_rows * d.dst_cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int dr = (int)(i / d.dst_cols), dc = (int)(i - (int64_t)dr * d.dst_cols);
+    const int lr = dr - d.row_off, lc = dc - d.col_off;
+    const int sr = d.transpose ? lc : lr, sc = d.transpose ? lr : lc;
+    float v = 0.f;
+    if (sr >= 0 && sc >= 0 && sr < d.rows && sc < d.cols)
+      v = d.scale * load_as_f(d.src, d.src_dtype, (int64_t)sr * d.src_ld + sc);
+    const int64_t o = (int64_t)dr * d.dst_ld + dc;
+    if (d.dst_dtype == UB200_BF16) reinterpret_cast<__nv_bfloat16*>(d.dst)[o] = __float2bfloat16_rn(v);
+    else if (d.dst_dtype == UB200_F16) reinterpret_cast<__half*>(d.dst)[o] = __float2half_rn(v);
+    else reinterpret_cast<float*>(d.dst)[o] = v;
+  }
+}
+
+// dst[r, c] (contiguous fp32) += src[r * src_rs + c * src_cs]
+__global__ void __launch_bounds__(256) accumulate_multi_kernel(const __grid_constant__ AccBatch b) {
+  const ub200_acc_desc& d = b.d[blockIdx.y];
+  const int64_t total = (int64_t)d.rows * d.cols;
+  // walk the SOURCE's fast axis with consecutive threads when it is the transposed one
+  const bool src_row_fast = d.src_rs == 1 && d.src_cs != 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int r, c;
+    if (src_row_fast) { c = (int)(i / d.rows); r = (int)(i - (int64_t)c * d.rows); }
+    else { r = (int)(i / d.cols); c = (int)(i - (int64_t)r * d.cols); }
+    const int64_t o = (int64_t)r * d.cols + c;
+    d.dst[o] += d.src[(int64_t)r * d.src_rs + (int64_t)c * d.src_cs];
+  }
+}
+
 }  // namespace ub
 
 extern "C" int ub200_abi_version(void) { return 1; }
+
+extern "C" int ub200_cast_pad_multi(const ub200_cast_desc* descs, int n, cudaStream_t stream) {
+  using namespace ub;
+  if (n <= 0) return UB200_OK;
+  if (!descs) return UB200_ERR_BAD_ARG;
+  for (int i0 = 0; i0 < n; i0 += MULTI_CHUNK) {
+    CastBatch b;
+    const int m = n - i0 < MULTI_CHUNK ? n - i0 : MULTI_CHUNK;
+    for (int i = 0; i < m; ++i) {
+      b.d[i] = descs[i0 + i];
+      if (!b.d[i].src || !b.d[i].dst || b.d[i].dst_rows <= 0 || b.d[i].dst_cols <= 0) return UB200_ERR_BAD_ARG;
+    }
+    cast_pad_multi_kernel<<<dim3(MULTI_CTAS, m), 256, 0, stream>>>(b);
+  }
+  UB_RETURN_LAST();
+}
+
+extern "C" int ub200_accumulate_multi(const ub200_acc_desc* descs, int n, cudaStream_t stream) {
+  using namespace ub;
+  if (n <= 0) return UB200_OK;
+  if (!descs) return UB200_ERR_BAD_ARG;
+  for (int i0 = 0; i0 < n; i0 += MULTI_CHUNK) {
+    AccBatch b;
+    const int m = n - i0 < MULTI_CHUNK ? n - i0 : MULTI_CHUNK;
+    for (int i = 0; i < m; ++i) {
+      b.d[i] = descs[i0 + i];
+      if (!b.d[i].src || !b.d[i].dst || b.d[i].rows <= 0 || b.d[i].cols <= 0) return UB200_ERR_BAD_ARG;
+    }
+    accumulate_multi_kernel<<<dim3(MULTI_CTAS, m), 256, 0, stream>>>(b);
+  }
+  UB_RETURN_LAST();
+}
 
 extern "C" int ub200_cast_pad_2d(const void* src, int src_dtype, int64_t src_ld, int rows, int cols,
                                  void* dst, int dst_dtype, int64_t dst_ld, int dst_rows,

@@ -61,12 +61,34 @@ class FlatLoRABucket:
             off += sz
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.t = 0
+        self.plan = None
 
     def numel(self):
         return self.flat_p.numel()
 
     def zero_grad(self):
         self.flat_g.zero_()
+
+    # -- batched step housekeeping (kernels/utils.py::StepPlan) ---------------------------------
+    def begin_step(self):
+        """zero_grad + (from the second step on) ONE batched refresh of every LoRA cast the step will use;
+        until `end_backward()` the projections' d_A / d_B bypass autograd's 448 AccumulateGrad launches."""
+        from .kernels import utils as KU
+        if self.plan is None:
+            self.plan = KU.StepPlan(self.params)
+        self.zero_grad()
+        KU.ACTIVE_PLAN = self.plan
+        self.plan.in_step = True
+        self.plan.refresh()
+
+    def end_backward(self):
+        """After `loss.backward()`: add the collected LoRA gradients into the bucket (batched launches)."""
+        from .kernels import utils as KU
+        if self.plan is not None:
+            self.plan.flush_grads()
+            self.plan.in_step = False
+        if KU.ACTIVE_PLAN is self.plan:
+            KU.ACTIVE_PLAN = None
 
     def broadcast_params(self, src=0):
         if dist.is_initialized() and dist.get_world_size() > 1:

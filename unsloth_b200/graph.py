@@ -40,9 +40,12 @@ class GraphedTrainStep:
         self.launches_per_replay = L.launch_count - n0
 
     def _fwd_bwd(self):
-        self.bucket.zero_grad()
-        out = self.model(input_ids=self.ids, labels=self.labels)
-        out.loss.backward()
+        self.bucket.begin_step()             # zero_grad + batched LoRA cast refresh
+        try:
+            out = self.model(input_ids=self.ids, labels=self.labels)
+            out.loss.backward()
+        finally:
+            self.bucket.end_backward()       # batched accumulation of the LoRA gradients
         self.loss = out.loss.detach()
 
     def step(self, input_ids, labels):

@@ -22,7 +22,8 @@ import os
 import torch
 
 from .. import _lib as L
-from .utils import (GradModeAware, Problem, RANK_BLOCK, fused_dequant_enabled, gemm_grouped, gemm_nf4, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
+from . import utils as KU
+from .utils import (GradModeAware, Problem, RANK_BLOCK, sink_lora_grads, fused_dequant_enabled, gemm_grouped, gemm_nf4, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
                     keep_dequant, keep_for_backward, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
                     matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
@@ -147,18 +148,28 @@ class _Group:
             ver = tuple((A._version, A.data_ptr()) for _, A in blocks) + (_epoch(),)
             cache = first.__dict__.setdefault("_ub200_acat_cache", {}) if isinstance(first, torch.nn.Parameter) else None
             key = (self.Rp, self.in_f, self.dtype, tuple(o for o, _ in blocks))
+            plan = KU.ACTIVE_PLAN
+            if plan is not None and plan.in_step:
+                hit = plan.lookup(first, ("acat",) + key)     # rebuilt by plan.refresh() at the start of this step
+                if hit is not None:
+                    self._A_cat = hit
+                    return self._A_cat
             if cache is not None and not refresh:
                 hit = cache.get(key)
                 if hit is not None and hit[0] == ver:
                     self._A_cat = hit[1]
                     return self._A_cat
             A_cat = torch.empty((self.Rp, self.in_f), dtype=self.dtype, device=self.dev)
+            parts = []
             for j, (o, A) in enumerate(blocks):
                 end = blocks[j + 1][0] if j + 1 < len(blocks) else self.Rp
                 A = A if A.stride(-1) == 1 else A.contiguous()
                 cast_pad(A, A_cat[o:end])
+                parts.append((A, A_cat[o:end]))
             if cache is not None:
                 cache[key] = (ver, A_cat)
+            if plan is not None and plan.in_step:
+                plan.record(first, ("acat",) + key, A_cat, parts)
             self._A_cat = A_cat
         return self._A_cat
 
@@ -324,7 +335,7 @@ class _Group:
                     grads.append((None, None))
                     continue
                 r = A.shape[0]
-                grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
+                grads.append(sink_lora_grads(A, B, dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
             return dX, grads
         return front, dense, tail, finish
 
@@ -376,7 +387,7 @@ class _Group:
                     grads.append((None, None))
                     continue
                 r = A.shape[0]
-                grads.append((dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
+                grads.append(sink_lora_grads(A, B, dA_catT[:, off:off + r].t(), dB_full[:, off:off + r]))
         else:
             grads = [(None, None)] * len(self.projs)
         if not need_dX:
@@ -479,7 +490,7 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
             dB_full = torch.empty((Hout, down.Rp), dtype=torch.float32, device=dev)
             gemm(Hout, down.Rp, [(dY2, XA2, T)], dB_full, a_mn=True, b_mn=True, alpha=downS,
                  split_k=_split_k(Hout, down.Rp, T))
-            d_downA, d_downB = dA_T[:, :r].t(), dB_full[:, :r]
+            d_downA, d_downB = sink_lora_grads(downA, downB, dA_T[:, :r].t(), dB_full[:, :r])
         # --- gate / up: LoRA grads and dX (into the saved X buffer when inplace)   (:178-204)
         grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
         grp.dense = dense_gu
@@ -541,7 +552,7 @@ def _mlp_backward_grouped(ctx, dY2, X2, e, g, XA1, XA2):
     d_downA = d_downB = None
     if downA is not None:
         r = downA.shape[0]
-        d_downA, d_downB = dA_T[:, :r].t(), dB_full[:, :r]
+        d_downA, d_downB = sink_lora_grads(downA, downB, dA_T[:, :r].t(), dB_full[:, :r])
     return (dX.view(ctx.shape), None, None, d_gateA, d_gateB, None, None, None, d_upA, d_upB,
             None, None, None, d_downA, d_downB, None, None, None, None)
 

@@ -410,6 +410,110 @@ except Exception:  # pragma: no cover - very old torch
     pass
 
 
+class StepPlan:
+    """Batched housekeeping of a bucketed training step (opt-in: `FlatLoRABucket.begin_step()` /
+    `end_backward()`, used by `GraphedTrainStep`, `bench.py` and `smoke()`).  A Llama-3-8B step makes 448
+    LoRA casts and hands 448 LoRA gradients to autograd's AccumulateGrad, each a 4-5 us launch (1.8 % of
+    the step, profiles/r2_launches_bench_full_summary.txt).  With a plan:
+      * casts: every cast `cached_cast_pad` makes of a LoRA Parameter during the first step is
+        remembered with its destination; `refresh()` rebuilds ALL of them at the start of each later step
+        (ub200_cast_pad_multi: one launch per 40 tensors) and the calls inside that step return the
+        refreshed buffers.  Outside `in_step` nothing changes: every forward still rebuilds its casts.
+      * gradients: d_A / d_B of a parameter whose `.grad` is a preallocated contiguous fp32 tensor (the
+        flat bucket) are collected instead of being returned to autograd and added by `flush_grads()`
+        (ub200_accumulate_multi) -- the same `grad += view` arithmetic, bit for bit."""
+
+    def __init__(self, params):
+        self.param_ids = {id(p) for p in params}
+        self.entries = {}            # (id(src), key) -> [src, key, dst, stamp, parts]
+        self.stamp = 0
+        self.in_step = False
+        self.recorded = False
+        self._cast_arr = None
+        self.grad_pairs = []
+
+    # -- casts ---------------------------------------------------------------------------------
+    def lookup(self, src, key):
+        ent = self.entries.get((id(src), key))
+        if ent is not None and ent[3] == self.stamp and ent[0] is src:
+            return ent[2]
+        return None
+
+    def record(self, src, key, dst, parts=None):
+        """dst was just built from `src` (key = the cast's arguments); parts: [(src_j, dst_view_j)] when several
+        adapters are cast into row slices of one shared block (plain casts, no offset / scale)."""
+        if parts is None:
+            shape, dtype, row_off, col_off, scale, transpose = key
+            parts = [(src, dst, row_off, col_off, scale, transpose)]
+        else:
+            parts = [(a, v, 0, 0, 1.0, False) for a, v in parts]
+        if all(id(a) in self.param_ids and a.dim() == 2 and a.stride(1) == 1 for a, *_ in parts):
+            self.entries[(id(src), key)] = [src, key, dst, self.stamp, parts]
+            self._cast_arr = None
+
+    def refresh(self):
+        """Start of a step: rebuild every recorded cast from the current parameter values."""
+        self.stamp += 1
+        if not self.entries:
+            return
+        if self._cast_arr is None:
+            ents = list(self.entries.values())
+            parts = [pt for e in ents for pt in e[4]]
+            arr = (L.CastDesc * len(parts))()
+            for d, (src, dst, row_off, col_off, scale, transpose) in zip(arr, parts):
+                d.src, d.dst = src.data_ptr(), dst.data_ptr()
+                d.src_ld, d.dst_ld = src.stride(0), dst.stride(0)
+                d.src_dtype, d.dst_dtype = L.dt(src), L.dt(dst)
+                d.rows, d.cols = src.shape[0], src.shape[1]
+                d.dst_rows, d.dst_cols = dst.shape[0], dst.shape[1]
+                d.row_off, d.col_off, d.scale, d.transpose = int(row_off), int(col_off), float(scale), int(transpose)
+            self._cast_arr = (arr, ents, parts)
+        arr, ents, parts = self._cast_arr
+        for d, (src, dst, *_r) in zip(arr, parts):
+            if src.data_ptr() != d.src or src.stride(0) != d.src_ld:
+                raise RuntimeError("unsloth_b200.StepPlan: a recorded LoRA parameter moved or changed layout")
+        L.call("ub200_cast_pad_multi", arr, len(parts), L.stream())
+        L.launch_count += (len(parts) - 1) // 40
+        for e in ents:
+            e[3] = self.stamp
+
+    # -- gradients -----------------------------------------------------------------------------
+    def sink(self, param, view):
+        g = getattr(param, "grad", None)
+        if (not self.in_step or view is None or id(param) not in self.param_ids or g is None
+                or g.dtype != torch.float32 or view.dtype != torch.float32 or not g.is_contiguous()
+                or g.shape != view.shape or view.dim() != 2):
+            return False
+        self.grad_pairs.append((view, g))
+        return True
+
+    def flush_grads(self):
+        n = len(self.grad_pairs)
+        if not n:
+            return
+        arr = (L.AccDesc * n)()
+        for d, (view, g) in zip(arr, self.grad_pairs):
+            d.src, d.dst = view.data_ptr(), g.data_ptr()
+            d.src_rs, d.src_cs = view.stride(0), view.stride(1)
+            d.rows, d.cols = g.shape[0], g.shape[1]
+        L.call("ub200_accumulate_multi", arr, n, L.stream())
+        L.launch_count += (n - 1) // 40
+        self.grad_pairs = []
+
+
+ACTIVE_PLAN = None
+
+
+def sink_lora_grads(A, B, dA, dB):
+    """(dA, dB) as autograd outputs -- or (None, None) when the active StepPlan took them."""
+    plan = ACTIVE_PLAN
+    if plan is not None and plan.in_step and plan.sink(A, dA):
+        if plan.sink(B, dB):
+            return None, None
+        return None, dB
+    return dA, dB
+
+
 def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpose=False,
                     refresh=False):
     """`cast_pad` into a fresh [shape] tensor, memoised ON the source nn.Parameter so that the
@@ -420,6 +524,11 @@ def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpos
                         scale, transpose)
     cache = src.__dict__.setdefault("_ub200_cast_cache", {})
     key = (tuple(shape), dtype, row_off, col_off, float(scale), bool(transpose))
+    plan = ACTIVE_PLAN
+    if plan is not None and plan.in_step:
+        dst = plan.lookup(src, key)          # rebuilt by plan.refresh() at the start of THIS step
+        if dst is not None:
+            return dst
     ver = (src._version, PARAM_EPOCH, src.data_ptr())
     hit = None if refresh else cache.get(key)
     if hit is not None and hit[0] == ver:
@@ -427,6 +536,8 @@ def cached_cast_pad(src, shape, dtype, row_off=0, col_off=0, scale=1.0, transpos
     dst = cast_pad(src, torch.empty(shape, dtype=dtype, device=src.device), row_off, col_off, scale,
                    transpose)
     cache[key] = (ver, dst)
+    if plan is not None and plan.in_step and src.dim() == 2 and src.stride(1) == 1:
+        plan.record(src, key, dst)
     return dst
 
 
