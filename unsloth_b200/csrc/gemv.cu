@@ -302,8 +302,6 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
                  : "r"(ring_lane + slot * GEMV_STAGE_BYTES));
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u1[0]), "=r"(u1[1]), "=r"(u1[2]), "=r"(u1[3])
                  : "r"(ring_lane + slot * GEMV_STAGE_BYTES + 8 * GEMV_ROW_STRIDE));
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty(slot));           // the slot is free once every warp holds its bytes in registers
     float d[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulation chains
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -320,6 +318,10 @@ __global__ void __launch_bounds__(288, 3) gemv_nf4_pair_kernel(
       if (i & 1) MmaOp<T>::mma(e, a, xb[2 * i], xb[2 * i + 1]);
       else MmaOp<T>::mma(d, a, xb[2 * i], xb[2 * i + 1]);
     }
+    // the slot is released only here: every (volatile, ordered) table lookup above consumed the registers the two
+    // LDS.128 filled, so the ring bytes have certainly been read before the producer may overwrite them
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty(slot));
     const float mine = absmax_f32 ? __uint_as_float(sq_now) : fmaf(code2_s[sq_now], a2, off);
     const float sc0 = __shfl_sync(0xffffffffu, mine, src0), sc1 = __shfl_sync(0xffffffffu, mine, src1);
     // D columns 2t, 2t+1 = segments 2t, 2t+1 = ONE absmax block (>= 64 columns); columns >= 4 are zero

@@ -74,9 +74,11 @@ class FlatLoRABucket:
         """zero_grad + (from the second step on) ONE batched refresh of every LoRA cast the step will use;
         until `end_backward()` the projections' d_A / d_B bypass autograd's 448 AccumulateGrad launches."""
         from .kernels import utils as KU
+        self.zero_grad()
+        if os.environ.get("UB200_STEP_PLAN", "1") in ("0", "off", "false"):     # A/B: per-tensor launches + autograd
+            return
         if self.plan is None:
             self.plan = KU.StepPlan(self.params)
-        self.zero_grad()
         KU.ACTIVE_PLAN = self.plan
         self.plan.in_step = True
         self.plan.refresh()
