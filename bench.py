@@ -432,6 +432,9 @@ def run_ours(args):
                        "attention": "UB200_ATTENTION=%s (auto: csrc/attention.cu for window / softcap / packed rows / D=256, "
                                     "cuDNN SDPA for plain dense causal)" % os.environ.get("UB200_ATTENTION", "auto"),
                        "step_plan": os.environ.get("UB200_STEP_PLAN", "1") not in ("0", "off", "false"),
+                       "glu_epilogue": "UB200_FUSED_GLU=%s (1: SwiGLU / GEGLU forward in the up projection's GEMM "
+                                       "epilogue, backward in the DW GEMM's; 0: separate elementwise launches)"
+                                       % os.environ.get("UB200_FUSED_GLU", "1"),
                        "l2_policy": "inputs larger than L2 (each step streams > 5 GB of NF4 weights and activations)"},
             "e2e": {"value": round(e2e, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 2),
                     "h2d_bytes_per_step": 2 * args.bs * args.seq * 8, "d2h_bytes_per_step": 4},

@@ -197,6 +197,23 @@ int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_m
                cudaStream_t stream);
 int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* bytes);
 
+/* ---- tcgen05 GEMM with the gated activation in its epilogue -----------------------------------
+ * The two places where LoRA_MLP runs an elementwise kernel straight after a projection
+ * (unsloth/kernels/fast_lora.py:84-87 forward, :155-157 backward) as ONE launch: the fp32
+ * accumulator tile is rounded to `dtype` exactly where the reference's matmul output is, then the
+ * per-element code of ub200_glu_fwd / ub200_glu_bwd runs on it in registers (same bits as the
+ * two-launch form).  Operand conventions as ub200_gemm; no split-K, no accumulate; `dtype` (bf16 /
+ * fp16) is the operand AND output dtype; C, e, g 16-byte aligned, ldc and ld_eg multiples of 8, N a multiple of 32 (else UB200_ERR_UNSUPPORTED).
+ *   mode UB200_GLU_EPI_FWD: acc = up projection.   g <- acc,  C <- act(e).to(dtype) * g   (e read only:
+ *                           the gate projection written by the previous launch)
+ *   mode UB200_GLU_EPI_BWD: acc = DW = dY @ W_down (+ LoRA).  C <- h = f(e) * g,  e <- df = DW * f,
+ *                           g <- de  (swiglu.py:86-109, geglu.py:74-123, 214-244: DW / e / g reuse)    */
+#define UB200_GLU_EPI_FWD 1
+#define UB200_GLU_EPI_BWD 2
+int ub200_gemm_glu(int mode, int act, int M, int N, const ub200_gemm_segment* segs, int n_segs,
+                   int a_mn_major, int b_mn_major, int dtype, void* C, int64_t ldc, void* e, void* g,
+                   int64_t ld_eg, float alpha, int block_n, int cta_group, cudaStream_t stream);
+
 /* ---- grouped tcgen05 GEMM: one persistent launch for a whole phase of a LoRA projection group --
  * All GEMMs the reference issues for one phase of LoRA_MLP / LoRA_QKV / LoRA_W (forward: X@A, the
  * dense products with the rank update; backward: dY@B, the dX sum, and the dA / dB reductions over

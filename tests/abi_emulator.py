@@ -168,6 +168,23 @@ def gemm(M, N, segs, n_segs, a_mn, b_mn, abdt, C, ldc, cdt, alpha, accumulate, s
     Cv.copy_(acc.to(_DT[cdt]))
 
 
+def gemm_glu(mode, act, M, N, segs, n_segs, a_mn, b_mn, dt, C, ldc, e, g, ld_eg, alpha, block_n, cta_group,
+             stream):
+    """ub200_gemm_glu: the GEMM, rounded to `dt`, then the gated activation on the tile (header contract)."""
+    assert mode in (1, 2) and N % 32 == 0 and ldc % 8 == 0 and ld_eg % 8 == 0 and dt in (1, 2)
+    d = _DT[dt]
+    tile = torch.empty(M, N, dtype=d)
+    gemm(M, N, segs, n_segs, a_mn, b_mn, dt, tile.data_ptr(), N, dt, alpha, 0, 1, None, block_n, cta_group,
+         stream)
+    Cv, ev, gv = view2d(C, d, M, N, ldc), view2d(e, d, M, N, ld_eg), view2d(g, d, M, N, ld_eg)
+    if mode == 1:      # forward: tile = up projection
+        gv.copy_(tile)
+        Cv.copy_(_GLU[act][0](ev.contiguous().view(1, M, N), tile.view(1, M, N)).view(M, N))
+    else:              # backward: tile = DW
+        hh, df, de = _GLU[act][1](tile.view(1, M, N), ev.contiguous().view(1, M, N), gv.contiguous().view(1, M, N))
+        Cv.copy_(hh.view(M, N)); ev.copy_(df.view(M, N)); gv.copy_(de.view(M, N))
+
+
 def gemm_grouped(probs, n_probs, abdt, scratch, stream):
     """Sequential interpretation of a grouped launch: problems in list order, so every in-launch
     dependency (wait_problem < own index) is already satisfied.  Checks the documented contract."""
@@ -240,6 +257,7 @@ _TABLE = {
     "ub200_rope_qk": rope_qk, "ub200_glu_fwd": glu_fwd, "ub200_glu_bwd": glu_bwd,
     "ub200_cross_entropy_fwd": cross_entropy_fwd, "ub200_cross_entropy_bwd": cross_entropy_bwd,
     "ub200_dequantize_nf4": dequantize_nf4, "ub200_quantize_nf4": quantize_nf4, "ub200_gemm": gemm, "ub200_gemm_grouped": gemm_grouped,
+    "ub200_gemm_glu": gemm_glu,
     "ub200_cast_pad_2d": cast_pad_2d, "ub200_gemv_nf4": gemv_nf4,
     "ub200_cast_pad_multi": cast_pad_multi, "ub200_accumulate_multi": accumulate_multi,
     "ub200_gemv_dense": gemv_dense,

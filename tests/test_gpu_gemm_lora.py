@@ -353,3 +353,101 @@ def test_fused_nf4_gemm_is_bit_identical_to_dequantise_then_gemm(T_, K, N, r):
     ref = gemm(T_, N, segs, torch.empty(T_, N, device=DEV, dtype=BF), cta_group=2, block_n=256)
     out = gemm_nf4(X, packed, qs, torch.empty(T_, N, device=DEV, dtype=BF), lora)
     assert torch.equal(out, ref), (out.float() - ref.float()).abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM with the gated activation in its epilogue (ub200_gemm_glu) -- must give the SAME BITS as the
+# two-launch form it replaces (ub200_gemm, then ub200_glu_fwd / ub200_glu_bwd).
+# ------------------------------------------------------------------------------------------------
+_GLU_FNS = {0: ("swiglu_fg_kernel", "swiglu_DWf_DW_dfg_kernel"),
+            1: ("geglu_approx_forward_kernel", "geglu_approx_backward_kernel"),
+            2: ("geglu_exact_forward_kernel", "geglu_exact_backward_kernel")}
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K,bn,cg,b_mn", [(256, 512, 256, 0, 0, True), (304, 224, 136, 0, 1, False),
+                                              (1000, 1024, 520, 256, 2, True), (640, 384, 264, 128, 2, True),
+                                              (136, 64, 72, 64, 1, False), (2048, 2816, 1088, 0, 0, True)])
+def test_gemm_glu_epilogue_bit_identical_to_two_launches(dtype, act, M, N, K, bn, cg, b_mn):
+    import unsloth_b200.kernels as KM
+    from unsloth_b200 import _lib as L
+    from unsloth_b200.kernels.utils import gemm, gemm_glu
+    torch.manual_seed(M + N + K + act)
+    r = 64
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(dtype)
+    B = (torch.randn(N, K, device=DEV) * 0.1).to(dtype)
+    A2 = (torch.randn(M, r, device=DEV) * 0.3).to(dtype)          # second K segment (the rank block)
+    B2 = (torch.randn(N, r, device=DEV) * 0.1).to(dtype)
+    Bop, B2op = (B.t().contiguous(), B2.t().contiguous()) if b_mn else (B, B2)
+    segs = [(A, Bop, K), (A2, B2op, r)]
+    e0 = (torch.randn(M, N, device=DEV) * 2).to(dtype)
+    g0 = torch.randn(M, N, device=DEV).to(dtype)
+    fwd_fn, bwd_fn = (getattr(KM, n) for n in _GLU_FNS[act])
+    # ---- backward: tile = DW
+    DW = torch.empty(M, N, device=DEV, dtype=dtype)
+    gemm(M, N, segs, DW, b_mn=b_mn, block_n=bn, cta_group=cg)
+    e1, g1 = e0.clone(), g0.clone()
+    h_ref, df_ref, de_ref = bwd_fn(DW, e1, g1)
+    e2, g2 = e0.clone(), g0.clone()
+    h = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
+    gemm_glu(L.GLU_EPI_BWD, act, M, N, segs, h, e2, g2, b_mn=b_mn, block_n=bn, cta_group=cg)
+    for name, a, b in (("h", h, h_ref), ("df", e2, df_ref), ("de", g2, de_ref)):
+        assert torch.equal(a, b), "%s: %d of %d elements differ" % (name, (a != b).sum().item(), a.numel())
+    # ---- forward: tile = up projection, e = gate projection (read only)
+    up = torch.empty(M, N, device=DEV, dtype=dtype)
+    gemm(M, N, segs, up, b_mn=b_mn, block_n=bn, cta_group=cg)
+    h_ref = fwd_fn(e0.view(1, M, N), up.view(1, M, N)).view(M, N)
+    e3 = e0.clone()
+    g3 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
+    h3 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
+    gemm_glu(L.GLU_EPI_FWD, act, M, N, segs, h3, e3, g3, b_mn=b_mn, block_n=bn, cta_group=cg)
+    assert torch.equal(g3, up) and torch.equal(e3, e0)
+    assert torch.equal(h3, h_ref), "%d of %d elements differ" % ((h3 != h_ref).sum().item(), h3.numel())
+
+
+def test_gemm_glu_rejects_what_it_cannot_do():
+    from unsloth_b200 import _lib as L
+    from unsloth_b200.kernels.utils import gemm_glu
+    A = torch.randn(128, 64, device=DEV).to(BF)
+    B = torch.randn(40, 64, device=DEV).to(BF)
+    e = torch.zeros(128, 40, device=DEV, dtype=BF)
+    with pytest.raises(RuntimeError):          # N % 32 != 0 -> UB200_ERR_UNSUPPORTED
+        gemm_glu(L.GLU_EPI_BWD, 0, 128, 40, [(A, B, 64)], torch.empty_like(e), e, e.clone())
+
+
+@pytest.mark.parametrize("act", ["swiglu", "geglu_approx"])
+def test_lora_mlp_fused_glu_equals_two_launch_schedule(act, monkeypatch):
+    """LoRA_MLP forward + backward at the cfg2 layer widths (H 4096, I 14336, NF4 base, r 16, T 1024) with
+    the GLU epilogues on (default) and off: every output and gradient must be bit-identical, except that
+    the forward with UB200_FUSED_GLU=1 takes the one-launch-per-GEMM schedule (not the grouped launch),
+    whose tile order does not change any accumulation order either."""
+    import unsloth_b200.kernels as K
+    from unsloth_b200.nf4 import quantize_nf4
+    torch.manual_seed(5)
+    Tn, H, I, r, s = 1024, 4096, 14336, 16, 2.0
+    fwd, bwd = (K.swiglu_fg_kernel, K.swiglu_DWf_DW_dfg_kernel) if act == "swiglu" else \
+        (K.geglu_approx_forward_kernel, K.geglu_approx_backward_kernel)
+
+    def mk(o, i):
+        W = (torch.randn(o, i, device=DEV) * 0.02).to(BF)
+        A = ((torch.rand(r, i, device=DEV) * 2 - 1) / i ** 0.5)
+        B = torch.randn(o, r, device=DEV) * 0.02
+        return quantize_nf4(W), A, B
+    (gq, gA, gB), (uq, uA, uB), (dq, dA, dB) = mk(I, H), mk(I, H), mk(H, I)
+    X = torch.randn(1, Tn, H, device=DEV).to(BF)
+    dY = (torch.randn(1, Tn, H, device=DEV) * 0.1).to(BF)
+
+    def run(flag):
+        monkeypatch.setenv("UB200_FUSED_GLU", flag)
+        P = [t.clone().requires_grad_() for t in (gA, gB, uA, uB, dA, dB)]
+        Xg = X.clone().requires_grad_()
+        out = K.LoRA_MLP.apply(Xg * 1.0, gq[0], gq[1], P[0], P[1], s, uq[0], uq[1], P[2], P[3], s,
+                               dq[0], dq[1], P[4], P[5], s, fwd, bwd, True)
+        out.backward(dY)
+        return [out.detach(), Xg.grad] + [p.grad for p in P]
+    fused, plain = run("1"), run("0")
+    names = ["out", "dX", "d_gateA", "d_gateB", "d_upA", "d_upB", "d_downA", "d_downB"]
+    for n, a, b in zip(names, fused, plain):
+        assert torch.equal(a, b), "%s: %d of %d elements differ (max |diff| %g)" % (
+            n, (a != b).sum().item(), a.numel(), (a.float() - b.float()).abs().max().item())

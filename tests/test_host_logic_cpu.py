@@ -704,3 +704,31 @@ def test_step_plan_batches_casts_and_gradient_accumulation(cpu_model, emu, name,
     del emu[:]
     model(input_ids=ids, labels=ids)
     assert "ub200_cast_pad_2d" in emu and "ub200_cast_pad_multi" not in emu
+
+
+@pytest.mark.parametrize("name,dtype", [("llama-3-8b", torch.bfloat16), ("gemma-2-9b", torch.float16)])
+def test_glu_epilogue_schedule_matches_two_launch_schedule(cpu_model, emu, monkeypatch, name, dtype):
+    """Host logic of the fused gated activation (ub200_gemm_glu, default for 16-bit tensors): the up
+    projection's launch leaves g and h, the DW launch overwrites e / g with df / de in place.  Same loss and
+    the same LoRA gradients as the two-launch schedule (UB200_FUSED_GLU=0), and the fused entry point is
+    what actually ran."""
+    P = cpu_model
+    extra = {"query_pre_attn_scalar": 16, "sliding_window": 8} if name.startswith("gemma") else {}
+    ids = torch.randint(0, TINY["vocab_size"], (2, 12), generator=torch.Generator().manual_seed(3))
+    res = {}
+    for flag in ("1", "0", "fwd", "bwd"):
+        monkeypatch.setenv("UB200_FUSED_GLU", flag)
+        torch.manual_seed(0)
+        m = _build(P, name, dtype=dtype, **extra)
+        del emu[:]
+        loss = m(input_ids=ids, labels=ids).loss
+        loss.backward()
+        n_fused = sum(1 for c in emu if c == "ub200_gemm_glu")
+        n_plain = sum(1 for c in emu if c in ("ub200_glu_fwd", "ub200_glu_bwd"))
+        res[flag] = (loss.detach().float(), _grads(P, m), n_fused, n_plain)
+    layers = 2
+    assert res["1"][2:] == (2 * layers, 0) and res["0"][2:] == (0, 2 * layers)
+    assert res["fwd"][2:] == (layers, layers) and res["bwd"][2:] == (layers, layers)
+    for flag in ("0", "fwd", "bwd"):
+        assert torch.equal(res["1"][0], res[flag][0])
+        torch.testing.assert_close(res["1"][1], res[flag][1], rtol=0, atol=0)

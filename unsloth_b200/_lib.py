@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("UB200_LIB_PATH") or os.path.join(_HERE, "_C", "libuns
 F32, F16, BF16 = 0, 1, 2
 ACT_SWIGLU, ACT_GEGLU_APPROX, ACT_GEGLU_EXACT = 0, 1, 2
 GEMM_MAX_SEGMENTS = 8
+GLU_EPI_FWD, GLU_EPI_BWD = 1, 2
 
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -95,6 +96,8 @@ _SIGS = {
     "ub200_gemm": ([_i, _i, POINTER(GemmSegment), _i, _i, _i, _i, _p, _l, _i, _f, _i, _i, _p, _i,
                     _i, _p], c_int),
     "ub200_gemm_workspace_bytes": ([_i, _i, _i, POINTER(c_int64)], c_int),
+    "ub200_gemm_glu": ([_i, _i, _i, _i, POINTER(GemmSegment), _i, _i, _i, _i, _p, _l, _p, _p, _l, _f, _i, _i,
+                        _p], c_int),
     "ub200_gemm_grouped": ([POINTER(GemmProblem), _i, _i, _p, _p], c_int),
     "ub200_gemm_grouped_scratch_ints": ([POINTER(GemmProblem), _i, POINTER(c_int)], c_int),
     "ub200_gemm_nf4": ([_i, _i, _i, _p, _l, _p, _p, _p, _p, _p, _i, _i, _p, _l, _p, _l, _i, _p, _l, _i, _p], c_int),

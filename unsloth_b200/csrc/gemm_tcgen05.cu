@@ -22,6 +22,7 @@
 //
 // Roofline: tensor-bound; flops = 2*M*N*sum(K_s).
 #include "tcgen05.cuh"
+#include "glu_math.cuh"
 
 namespace ub {
 namespace gemm {
@@ -51,6 +52,12 @@ struct Params {
   int ab_fp16;           // operands are fp16 instead of bf16
   int raster_mode;       // 0: groups of `raster_group` M-tiles stay L2-resident, sweep N; 1: N-groups, sweep M
   int raster_group;
+  // gated-activation epilogue (kernels instantiated with EPI = 1, ub200_gemm_glu); 16-bit output only
+  int glu_mode;          // UB200_GLU_EPI_FWD / UB200_GLU_EPI_BWD
+  int glu_act;           // ACT_SWIGLU / ACT_GEGLU_APPROX / ACT_GEGLU_EXACT
+  void* glu_e;           // [M, N] fwd: read (gate output);      bwd: read e, overwritten with df
+  void* glu_g;           // [M, N] fwd: written (up output);     bwd: read g, overwritten with de
+  int64_t ld_eg;
 };
 
 // L2-aware rasterisation of the tile grid.  The two 63 MB L2 halves each keep their own copy of
@@ -146,6 +153,86 @@ __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&r)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Gated-activation epilogue (EPI = 1).  The accumulator tile never makes the round trip through HBM
+// that the two-kernel form (GEMM, then glu.cu) pays:
+//   backward (fast_lora.py:155-157 + swiglu.py:86-109 / geglu.py:214-244): the tile is DW = dY @ W_down
+//     (+ LoRA); it is rounded to the tensor dtype exactly where the reference's matmul output is, then
+//     h = f(e) * g -> C,  df = DW * f -> e's buffer,  de = (DW * g) * f'(e) -> g's buffer (in place);
+//   forward (fast_lora.py:84-87 + swiglu.py:37-47): the tile is g = X @ W_up (+ LoRA); e (the gate
+//     projection, written by the previous launch) is read, g is stored and h = f(e) * g -> C.
+// Same per-element code and rounding points as glu.cu (glu_math.cuh), so both forms give the same bits.
+// One thread owns one row: 32 consecutive columns = 64 contiguous bytes of every tensor per chunk.  The
+// operand loads are issued BEFORE the TMEM read so their latency overlaps it (and the previous chunk's
+// stores); they are evict-first, the operand tiles of the main loop own the L2.
+// ---------------------------------------------------------------------------------------
+struct GluRegs {
+  uint4 e[4];
+  uint4 g[4];
+};
+
+__device__ __forceinline__ void glu_prefetch(const Params& p, GluRegs& q, int row, int col0) {
+  if (col0 + 32 > p.N) return;                                  // never taken: the host requires N % 32 == 0
+  const uint16_t* ep = reinterpret_cast<const uint16_t*>(p.glu_e) + (int64_t)row * p.ld_eg + col0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q.e[i] = __ldcs(reinterpret_cast<const uint4*>(ep) + i);
+  if (p.glu_mode == UB200_GLU_EPI_BWD) {
+    const uint16_t* gp = reinterpret_cast<const uint16_t*>(p.glu_g) + (int64_t)row * p.ld_eg + col0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q.g[i] = __ldcs(reinterpret_cast<const uint4*>(gp) + i);
+  }
+}
+
+// element `hi` (0 / 1) of a packed pair of 16-bit values, as fp32 (register-only: no address is taken)
+template <typename T> __device__ __forceinline__ float unpack16(uint32_t w, int hi);
+template <> __device__ __forceinline__ float unpack16<__nv_bfloat16>(uint32_t w, int hi) {
+  return __uint_as_float(hi ? (w & 0xffff0000u) : (w << 16));
+}
+template <> __device__ __forceinline__ float unpack16<__half>(uint32_t w, int hi) {
+  return __half2float(__ushort_as_half((unsigned short)(hi ? (w >> 16) : (w & 0xffffu))));
+}
+
+template <typename T, int ACT>
+__device__ __forceinline__ void glu_finish_t(const Params& p, const uint32_t (&r)[32], const GluRegs& q,
+                                             bool has_k, int row, int col0) {
+  T* cp = reinterpret_cast<T*>(p.C) + (int64_t)row * p.ldc + col0;
+  T* ep = reinterpret_cast<T*>(p.glu_e) + (int64_t)row * p.ld_eg + col0;
+  T* gp = reinterpret_cast<T*>(p.glu_g) + (int64_t)row * p.ld_eg + col0;
+  const bool bwd = p.glu_mode == UB200_GLU_EPI_BWD;
+  if (col0 + 32 <= p.N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t ew[4] = {q.e[i].x, q.e[i].y, q.e[i].z, q.e[i].w};
+      const uint32_t gw[4] = {q.g[i].x, q.g[i].y, q.g[i].z, q.g[i].w};
+      float o0[8], o1[8], o2[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float acc = DT<T>::rnd(has_k ? __uint_as_float(r[8 * i + k]) * p.alpha : 0.f);
+        const float ek = unpack16<T>(ew[k >> 1], k & 1);
+        if (bwd) glu_bwd_elem<T, ACT>(acc, ek, unpack16<T>(gw[k >> 1], k & 1), o0[k], o1[k], o2[k]);
+        else { o0[k] = glu_fwd_elem<T, ACT>(ek, acc); o1[k] = 0.f; o2[k] = acc; }
+      }
+      store_vec<T>(cp + 8 * i, o0);                // h
+      if (bwd) store_vec<T>(ep + 8 * i, o1);       // df (in place over e)
+      store_vec<T>(gp + 8 * i, o2);                // de (in place over g) / g
+    }
+  }
+}
+
+__device__ __forceinline__ void glu_finish(const Params& p, const uint32_t (&r)[32], const GluRegs& q,
+                                           bool has_k, int row, int col0) {
+  if (p.c_dtype == UB200_BF16) {
+    if (p.glu_act == ACT_SWIGLU) glu_finish_t<__nv_bfloat16, ACT_SWIGLU>(p, r, q, has_k, row, col0);
+    else if (p.glu_act == ACT_GEGLU_APPROX) glu_finish_t<__nv_bfloat16, ACT_GEGLU_APPROX>(p, r, q, has_k, row, col0);
+    else glu_finish_t<__nv_bfloat16, ACT_GEGLU_EXACT>(p, r, q, has_k, row, col0);
+  } else {
+    if (p.glu_act == ACT_SWIGLU) glu_finish_t<__half, ACT_SWIGLU>(p, r, q, has_k, row, col0);
+    else if (p.glu_act == ACT_GEGLU_APPROX) glu_finish_t<__half, ACT_GEGLU_APPROX>(p, r, q, has_k, row, col0);
+    else glu_finish_t<__half, ACT_GEGLU_EXACT>(p, r, q, has_k, row, col0);
+  }
+}
+
+
 template <int BLOCK_N>
 struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
@@ -156,7 +243,7 @@ struct Cfg {
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ Params p) {
   using C = Cfg<BLOCK_N>;
@@ -315,9 +402,17 @@ gemm_kernel(const __grid_constant__ Params p) {
         if (col0 >= p.N) break;                   // warp-uniform
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
-        tmem_ld32(taddr, r);
-        tmem_ld_wait(r);
-        if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
+        if constexpr (EPI) {
+          GluRegs gq;
+          if (row_ok) glu_prefetch(p, gq, row, col0);
+          tmem_ld32(taddr, r);
+          tmem_ld_wait(r);
+          if (row_ok) glu_finish(p, r, gq, has_k, row, col0);
+        } else {
+          tmem_ld32(taddr, r);
+          tmem_ld_wait(r);
+          if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
+        }
       }
       // release the accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -355,7 +450,7 @@ struct Cfg2 {
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ Params p) {
   using C = Cfg2<BLOCK_N>;
@@ -520,9 +615,17 @@ gemm2_kernel(const __grid_constant__ Params p) {
         if (col0 >= p.N) break;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
-        tmem_ld32(taddr, r);
-        tmem_ld_wait(r);
-        if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
+        if constexpr (EPI) {
+          GluRegs gq;
+          if (row_ok) glu_prefetch(p, gq, row, col0);
+          tmem_ld32(taddr, r);
+          tmem_ld_wait(r);
+          if (row_ok) glu_finish(p, r, gq, has_k, row, col0);
+        } else {
+          tmem_ld32(taddr, r);
+          tmem_ld_wait(r);
+          if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -568,31 +671,31 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 static int launch(const Params& p, int grid, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  gemm_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
   return UB200_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 static int launch2(const Params& p, int grid, cudaStream_t st) {
   using C = Cfg2<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BLOCK_N>,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BLOCK_N, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm2_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);   // __cluster_dims__(2,1,1)
+  gemm2_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);   // __cluster_dims__(2,1,1)
   return UB200_OK;
 }
 
@@ -605,10 +708,16 @@ extern "C" int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* by
   return UB200_OK;
 }
 
-extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
-                          int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype,
-                          float alpha, int accumulate, int split_k, void* workspace,
-                          int block_n, int cta_group, cudaStream_t stream) {
+namespace ub {
+namespace gemm {
+struct GluArgs { int mode, act; void* e; void* g; int64_t ld_eg; };
+}  // namespace gemm
+}  // namespace ub
+
+static int gemm_impl(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
+                     int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype,
+                     float alpha, int accumulate, int split_k, void* workspace,
+                     int block_n, int cta_group, const ub::gemm::GluArgs* glu, cudaStream_t stream) {
   using namespace ub;
   using namespace ub::gemm;
   if (M <= 0 || N <= 0) return UB200_OK;
@@ -626,6 +735,9 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
 
   Params p;
   memset(&p, 0, sizeof(p));
+  if (glu) {
+    p.glu_mode = glu->mode; p.glu_act = glu->act; p.glu_e = glu->e; p.glu_g = glu->g; p.ld_eg = glu->ld_eg;
+  }
   p.n_segs = n_segs;
   p.M = M;
   p.N = N;
@@ -684,11 +796,16 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
     const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     const int num_work = m_pairs * p.n_tiles * split_k;
     int pairs = num_work < UB_SM_COUNT / 2 ? num_work : UB_SM_COUNT / 2;
-    rc = bn == 256 ? launch2<256>(p, 2 * pairs, stream) : launch2<128>(p, 2 * pairs, stream);
+    if (glu) rc = bn == 256 ? launch2<256, 1>(p, 2 * pairs, stream) : launch2<128, 1>(p, 2 * pairs, stream);
+    else rc = bn == 256 ? launch2<256>(p, 2 * pairs, stream) : launch2<128>(p, 2 * pairs, stream);
   } else {
     const int num_work = p.m_tiles * p.n_tiles * split_k;
     const int grid = num_work < UB_SM_COUNT ? num_work : UB_SM_COUNT;
-    if (bn == 256) rc = launch<256>(p, grid, stream);
+    if (glu) {
+      if (bn == 256) rc = launch<256, 1>(p, grid, stream);
+      else if (bn == 128) rc = launch<128, 1>(p, grid, stream);
+      else rc = launch<64, 1>(p, grid, stream);
+    } else if (bn == 256) rc = launch<256>(p, grid, stream);
     else if (bn == 128) rc = launch<128>(p, grid, stream);
     else rc = launch<64>(p, grid, stream);
   }
@@ -701,4 +818,32 @@ extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_se
                                                      split_k, C, ldc, c_dtype, accumulate, M, N, N);
   }
   UB_RETURN_LAST();
+}
+
+extern "C" int ub200_gemm(int M, int N, const ub200_gemm_segment* segs, int n_segs, int a_mn_major,
+                          int b_mn_major, int ab_dtype, void* C, int64_t ldc, int c_dtype,
+                          float alpha, int accumulate, int split_k, void* workspace,
+                          int block_n, int cta_group, cudaStream_t stream) {
+  return gemm_impl(M, N, segs, n_segs, a_mn_major, b_mn_major, ab_dtype, C, ldc, c_dtype, alpha, accumulate,
+                   split_k, workspace, block_n, cta_group, nullptr, stream);
+}
+
+extern "C" int ub200_gemm_glu(int mode, int act, int M, int N, const ub200_gemm_segment* segs, int n_segs,
+                              int a_mn_major, int b_mn_major, int dtype, void* C, int64_t ldc, void* e,
+                              void* g, int64_t ld_eg, float alpha, int block_n, int cta_group,
+                              cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return UB200_OK;
+  if (mode != UB200_GLU_EPI_FWD && mode != UB200_GLU_EPI_BWD) return UB200_ERR_BAD_ARG;
+  if (act != ub::ACT_SWIGLU && act != ub::ACT_GEGLU_APPROX && act != ub::ACT_GEGLU_EXACT)
+    return UB200_ERR_BAD_ARG;
+  if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_BAD_ARG;
+  if (!C || !e || !g) return UB200_ERR_BAD_ARG;
+  // the epilogue moves 16-byte vectors of 32-column chunks: every row of C / e / g must start 16-byte aligned
+  if ((reinterpret_cast<uintptr_t>(C) & 15) || (reinterpret_cast<uintptr_t>(e) & 15) ||
+      (reinterpret_cast<uintptr_t>(g) & 15) || (ldc % 8) || (ld_eg % 8) || ldc < N || ld_eg < N)
+    return UB200_ERR_BAD_ARG;
+  if (N % 32) return UB200_ERR_UNSUPPORTED;   // whole 32-column chunks only (the caller falls back to two launches)
+  ub::gemm::GluArgs ga{mode, act, e, g, ld_eg};
+  return gemm_impl(M, N, segs, n_segs, a_mn_major, b_mn_major, dtype, C, ldc, dtype, alpha, 0, 1, nullptr,
+                   block_n, cta_group, &ga, stream);
 }

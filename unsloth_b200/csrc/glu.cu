@@ -11,39 +11,13 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "glu_math.cuh"
 
 #ifndef UB200_GLU_DEFAULT_VARIANT
 #define UB200_GLU_DEFAULT_VARIANT 4
 #endif
 
 namespace ub {
-
-enum { ACT_SWIGLU = 0, ACT_GEGLU_APPROX = 1, ACT_GEGLU_EXACT = 2 };
-
-// returns f(e) (fp32, before rounding) and df/de.  FAST (16-bit tensors): the sigmoid uses the
-// MUFU exp2 / reciprocal path (relative error ~1e-6, far below the bf16/fp16 output rounding);
-// fp32 tensors keep the accurate expf and IEEE division so the 1e-5 gate holds.
-template <int ACT, bool FAST>
-__device__ __forceinline__ void act_eval(float e, float& f, float& dfde) {
-  if (ACT == ACT_SWIGLU) {
-    const float se = FAST ? __frcp_rn(1.0f + __expf(-e)) : 1.0f / (1.0f + expf(-e));
-    f = e * se;
-    dfde = se * (1.0f + e * (1.0f - se));
-  } else if (ACT == ACT_GEGLU_APPROX) {
-    const float s = 0.7978845608028654f;
-    const float a = s * e;
-    const float b = a * 0.044715f * e * e;
-    const float T = 1.0f + tanhf(a + b);
-    const float T2 = 0.5f * T;
-    const float Q2 = -T2 * (T - 2.0f) * (a + 3.0f * b);
-    f = T2 * e;
-    dfde = T2 + Q2;
-  } else {
-    const float fp = 0.5f * (erff(0.70710678118654752f * e) + 1.0f);
-    f = fp * e;
-    dfde = fp + 0.3989422804014327f * e * expf(-0.5f * e * e);
-  }
-}
 
 // Launch shape (measured, profiles/r2_glu_variants.log): the default is ONE-SHOT CTAs of 128 threads, one
 // 16-byte vector of every operand per thread -- the grid covers the tensor (114,688 CTAs at cfg2) and the

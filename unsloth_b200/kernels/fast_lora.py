@@ -24,6 +24,7 @@ import torch
 from .. import _lib as L
 from . import utils as KU
 from .utils import (GradModeAware, Problem, RANK_BLOCK, sink_lora_grads, fused_dequant_enabled, gemm_grouped, gemm_nf4, as_b_operand, cached_cast_pad, cast_pad, dense_weight, gemm,
+                    gemm_glu, glu_fusable, fused_glu_enabled,
                     keep_dequant, keep_for_backward, get_lora_parameters, get_lora_parameters_bias,  # noqa: F401
                     matmul_lora)  # noqa: F401
 from .swiglu import swiglu_fg_kernel, swiglu_DWf_DW_dfg_kernel
@@ -31,6 +32,12 @@ from .geglu import (geglu_exact_forward_kernel, geglu_exact_backward_kernel,
                     geglu_approx_forward_kernel, geglu_approx_backward_kernel)
 
 _SM = 148
+
+# the elementwise functions LoRA_MLP is called with (apply_lora_mlp_*) -> activation id of the GLU epilogue
+_GLU_FWD_ACT = {swiglu_fg_kernel: L.ACT_SWIGLU, geglu_approx_forward_kernel: L.ACT_GEGLU_APPROX,
+                geglu_exact_forward_kernel: L.ACT_GEGLU_EXACT}
+_GLU_BWD_ACT = {swiglu_DWf_DW_dfg_kernel: L.ACT_SWIGLU, geglu_approx_backward_kernel: L.ACT_GEGLU_APPROX,
+                geglu_exact_backward_kernel: L.ACT_GEGLU_EXACT}
 
 def _grouped():
     """UB200_GROUPED=0 falls back to one launch per GEMM (round-1 schedule; A/B measurements)."""
@@ -173,12 +180,18 @@ class _Group:
             self._A_cat = A_cat
         return self._A_cat
 
-    def forward(self, keep=False):
+    def forward(self, keep=False, glu_act=None):
         """Returns ([Y_i], XA) with XA = X @ A_cat^T  ([T, Rp], unscaled) or None.  `keep`: the
-        dequantised weights are private tensors left in `self.dense` for the backward."""
+        dequantised weights are private tensors left in `self.dense` for the backward.
+        `glu_act` (gate / up group of LoRA_MLP only): the LAST projection's launch applies the gated
+        activation in its epilogue -- h = act(Y_0) * Y_1 is left in `self.h` (ub200_gemm_glu)."""
+        self.h = None
         if fused_dequant_enabled() and self._fusable():
             return self._forward_fused_dequant()
-        if _fwd_grouped(self.kind):
+        if glu_act is not None and not (len(self.projs) == 2 and self.dtype in (torch.bfloat16, torch.float16)
+                                        and self.projs[0][0].shape[0] == self.projs[1][0].shape[0]):
+            glu_act = None
+        if glu_act is None and _fwd_grouped(self.kind):
             return self._forward_grouped(keep)
         X2, T, dt, dev = self.X2, self.T, self.dtype, self.dev
         if keep:
@@ -204,7 +217,12 @@ class _Group:
                     B_pad = cached_cast_pad(Bc, (N, self.Rp), dt, col_off=off, scale=s, refresh=True)
                 segs.append((XA, B_pad, self.Rp))
             Y = torch.empty((T, N), dtype=dt, device=dev)
-            gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
+            if glu_act is not None and len(outs) == 1 and glu_fusable(N, Y, outs[0]):
+                # up projection: g -> Y and h = act(e) * g in the same epilogue           (fast_lora.py:84-87)
+                self.h = torch.empty((T, N), dtype=dt, device=dev)
+                gemm_glu(L.GLU_EPI_FWD, glu_act, T, N, segs, self.h, outs[0], Y, a_mn=False, b_mn=b_mn)
+            else:
+                gemm(T, N, segs, Y, a_mn=False, b_mn=b_mn)
             outs.append(Y)
         return outs, XA
 
@@ -424,11 +442,16 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
         X2 = _as2d(X)
         grp = _Group(X2, [(gateW, gateW_quant, gateA, gateB, gateS), (upW, upW_quant, upA, upB, upS)])
         keep = keep_for_backward(ctx.needs_input_grad)
-        (e, g), XA1 = grp.forward(keep)
+        glu_act = _GLU_FWD_ACT.get(_forward_function) if fused_glu_enabled("fwd") else None
+        (e, g), XA1 = grp.forward(keep, glu_act=glu_act)
         b_s = shape[:-1]
-        h = _forward_function(e.view(*b_s, -1) if X.dim() == 3 else e.view(1, *e.shape),
-                              g.view(*b_s, -1) if X.dim() == 3 else g.view(1, *g.shape))
-        h2 = h.reshape(-1, h.shape[-1])
+        if grp.h is not None:
+            h2 = grp.h                               # produced by the up projection's epilogue
+            grp.h = None
+        else:
+            h = _forward_function(e.view(*b_s, -1) if X.dim() == 3 else e.view(1, *e.shape),
+                                  g.view(*b_s, -1) if X.dim() == 3 else g.view(1, *g.shape))
+            h2 = h.reshape(-1, h.shape[-1])
         grp2 = _Group(h2, [(downW, downW_quant, downA, downB, downS)])
         (i,), XA2 = grp2.forward(keep)
         ctx.dense = (grp.dense, grp2.dense)
@@ -475,9 +498,15 @@ class LoRA_MLP(GradModeAware, torch.autograd.Function):
                           torch.empty((T, down.Rp), dtype=dt, device=dev), b_mn=True)
             segs.append((G_down, down.A_cat(), down.Rp))
         DW = torch.empty((T, e.shape[1]), dtype=dt, device=dev)
-        gemm(T, e.shape[1], segs, DW, a_mn=False, b_mn=True)
-        # --- activation backward, in place: DW <- h, e <- df, g <- de            (:156-157)
-        h, df, de = _backward_function(DW, e, g)
+        glu_act = _GLU_BWD_ACT.get(_backward_function) if fused_glu_enabled("bwd") else None
+        if glu_act is not None and glu_fusable(e.shape[1], DW, e, g) and e.stride(0) == g.stride(0):
+            # DW never reaches HBM: the activation backward runs on the accumulator tile, in place over e / g
+            gemm_glu(L.GLU_EPI_BWD, glu_act, T, e.shape[1], segs, DW, e, g, a_mn=False, b_mn=True)
+            h, df, de = DW, e, g
+        else:
+            gemm(T, e.shape[1], segs, DW, a_mn=False, b_mn=True)
+            # --- activation backward, in place: DW <- h, e <- df, g <- de            (:156-157)
+            h, df, de = _backward_function(DW, e, g)
         # --- down LoRA grads                                                      (:171-172)
         d_downA = d_downB = None
         if downA is not None:

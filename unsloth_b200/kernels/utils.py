@@ -238,6 +238,58 @@ def gemm(M, N, segs, out, a_mn=False, b_mn=False, alpha=1.0, accumulate=False, s
     return out
 
 
+def fused_glu_enabled(direction) -> bool:
+    """UB200_FUSED_GLU: "1" (default) = the gated activation of LoRA_MLP runs in the epilogue of the
+    projection that feeds it (ub200_gemm_glu); "0" = two launches (round-1 schedule); "fwd" / "bwd" = one
+    direction only (A/B measurements)."""
+    v = os.environ.get("UB200_FUSED_GLU", "1")
+    return v == "1" or v == direction
+
+
+def glu_fusable(N, *tensors) -> bool:
+    """Conditions of ub200_gemm_glu: 16-bit row-major [T, N] tensors, whole 32-column chunks."""
+    if N % 32:
+        return False
+    for t in tensors:
+        if t.dtype not in (torch.bfloat16, torch.float16) or t.dim() != 2 or t.stride(1) != 1 \
+                or t.stride(0) % 8 or t.data_ptr() % 16:
+            return False
+    return True
+
+
+def gemm_glu(mode, act, M, N, segs, out, e, g, a_mn=False, b_mn=False, alpha=1.0, block_n=0, cta_group=0):
+    """ub200_gemm_glu: `gemm` whose epilogue applies the gated activation to the accumulator tile.
+    mode GLU_EPI_FWD: tile = up projection -> g, out = act(e) * g.  mode GLU_EPI_BWD: tile = DW;
+    out <- h, e <- df, g <- de (in place, the reference's buffer reuse)."""
+    n = len(segs)
+    arr = (L.GemmSegment * n)()
+    ab_dtype = segs[0][0].dtype
+    for i, sg in enumerate(segs):
+        A, B, K = sg[0], sg[1], sg[2]
+        _check_operand(A); _check_operand(B)
+        if A.dtype != ab_dtype or B.dtype != ab_dtype:
+            raise RuntimeError("unsloth_b200.gemm_glu: mixed operand dtypes %s/%s" % (A.dtype, B.dtype))
+        arr[i].a = A.data_ptr(); arr[i].lda = A.stride(0)
+        arr[i].b = B.data_ptr(); arr[i].ldb = B.stride(0)
+        arr[i].k = K
+    if not (out.dtype == e.dtype == g.dtype == ab_dtype) or e.stride(0) != g.stride(0):
+        raise RuntimeError("unsloth_b200.gemm_glu: C / e / g must share the operand dtype and e / g one row stride")
+    ev = GEMM_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("ub200_gemm_glu", int(mode), int(act), M, N, arr, n, int(a_mn), int(b_mn), L.dt(ab_dtype),
+           L.ptr(out), out.stride(0), L.ptr(e), L.ptr(g), e.stride(0), float(alpha), int(block_n),
+           int(cta_group), L.stream())
+    if ev is not None:
+        e1.record()
+        bn = block_n or (256 if N > 128 else (128 if N > 64 else 64))
+        pair = cta_group == 2 or (cta_group == 0 and bn >= 128 and M > 128)
+        ev.append((2.0 * M * N * sum(sg[3] if len(sg) > 3 else sg[2] for sg in segs), e0, e1,
+                   {"kernel": "gemm2" if pair else "gemm1", "epilogue": "glu"}))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # grouped GEMM: one persistent launch for a list of dependent problems (csrc/gemm_grouped.cu)
 # ---------------------------------------------------------------------------------------------
