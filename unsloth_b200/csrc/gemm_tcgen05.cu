@@ -31,6 +31,10 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 x 2 B = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
+// kernels with the gated-activation epilogue run EIGHT epilogue warps (two per TMEM lane quarter, interleaved
+// 32-column chunks): the epilogue streams 3-5x the bytes of a plain store and is latency-bound with four
+constexpr int NUM_THREADS_GLU = 320;
+__host__ __device__ constexpr int threads_of(int epi) { return epi ? NUM_THREADS_GLU : NUM_THREADS; }
 constexpr int MAX_SEGS = UB200_GEMM_MAX_SEGMENTS;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
 
@@ -167,19 +171,32 @@ __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&r)
 // stores); they are evict-first, the operand tiles of the main loop own the L2.
 // ---------------------------------------------------------------------------------------
 struct GluRegs {
-  uint4 e[4];
-  uint4 g[4];
+  uint32_t e[16];     // 32 consecutive 16-bit values of this thread's row
+  uint32_t g[16];
 };
+
+// 32-byte global accesses (sm_100: LDG.E.256 / STG.E.256): one thread moves a whole 32-byte sector per
+// instruction, so a row's 64-byte chunk is 2 requests instead of 4 half-sector ones.  Loads are evict-first.
+__device__ __forceinline__ void ldg256_cs(const void* ptr, uint32_t* r) {
+  asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 
 __device__ __forceinline__ void glu_prefetch(const Params& p, GluRegs& q, int row, int col0) {
   if (col0 + 32 > p.N) return;                                  // never taken: the host requires N % 32 == 0
   const uint16_t* ep = reinterpret_cast<const uint16_t*>(p.glu_e) + (int64_t)row * p.ld_eg + col0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) q.e[i] = __ldcs(reinterpret_cast<const uint4*>(ep) + i);
+  ldg256_cs(ep, q.e);
+  ldg256_cs(ep + 16, q.e + 8);
   if (p.glu_mode == UB200_GLU_EPI_BWD) {
     const uint16_t* gp = reinterpret_cast<const uint16_t*>(p.glu_g) + (int64_t)row * p.ld_eg + col0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q.g[i] = __ldcs(reinterpret_cast<const uint4*>(gp) + i);
+    ldg256_cs(gp, q.g);
+    ldg256_cs(gp + 16, q.g + 8);
   }
 }
 
@@ -191,6 +208,16 @@ template <> __device__ __forceinline__ float unpack16<__nv_bfloat16>(uint32_t w,
 template <> __device__ __forceinline__ float unpack16<__half>(uint32_t w, int hi) {
   return __half2float(__ushort_as_half((unsigned short)(hi ? (w >> 16) : (w & 0xffffu))));
 }
+// two floats -> one packed pair, round to nearest even (the rounding of DT<T>::from_f)
+template <typename T> __device__ __forceinline__ uint32_t pack16(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+template <> __device__ __forceinline__ uint32_t pack16<__half>(float lo, float hi) {
+  const __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 template <typename T, int ACT>
 __device__ __forceinline__ void glu_finish_t(const Params& p, const uint32_t (&r)[32], const GluRegs& q,
@@ -201,20 +228,25 @@ __device__ __forceinline__ void glu_finish_t(const Params& p, const uint32_t (&r
   const bool bwd = p.glu_mode == UB200_GLU_EPI_BWD;
   if (col0 + 32 <= p.N) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t ew[4] = {q.e[i].x, q.e[i].y, q.e[i].z, q.e[i].w};
-      const uint32_t gw[4] = {q.g[i].x, q.g[i].y, q.g[i].z, q.g[i].w};
-      float o0[8], o1[8], o2[8];
+    for (int i = 0; i < 2; ++i) {                    // 16 columns = one 32-byte sector of every tensor
+      uint32_t w0[8], w1[8], w2[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float acc = DT<T>::rnd(has_k ? __uint_as_float(r[8 * i + k]) * p.alpha : 0.f);
-        const float ek = unpack16<T>(ew[k >> 1], k & 1);
-        if (bwd) glu_bwd_elem<T, ACT>(acc, ek, unpack16<T>(gw[k >> 1], k & 1), o0[k], o1[k], o2[k]);
-        else { o0[k] = glu_fwd_elem<T, ACT>(ek, acc); o1[k] = 0.f; o2[k] = acc; }
+        float o0[2], o1[2], o2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float acc = DT<T>::rnd(has_k ? __uint_as_float(r[16 * i + 2 * k + j]) * p.alpha : 0.f);
+          const float ek = unpack16<T>(q.e[8 * i + k], j);
+          if (bwd) glu_bwd_elem<T, ACT>(acc, ek, unpack16<T>(q.g[8 * i + k], j), o0[j], o1[j], o2[j]);
+          else { o0[j] = glu_fwd_elem<T, ACT>(ek, acc); o1[j] = 0.f; o2[j] = acc; }
+        }
+        w0[k] = pack16<T>(o0[0], o0[1]);
+        w1[k] = pack16<T>(o1[0], o1[1]);
+        w2[k] = pack16<T>(o2[0], o2[1]);
       }
-      store_vec<T>(cp + 8 * i, o0);                // h
-      if (bwd) store_vec<T>(ep + 8 * i, o1);       // df (in place over e)
-      store_vec<T>(gp + 8 * i, o2);                // de (in place over g) / g
+      stg256(cp + 16 * i, w0);                       // h
+      if (bwd) stg256(ep + 16 * i, w1);              // df (in place over e)
+      stg256(gp + 16 * i, w2);                       // de (in place over g) / g
     }
   }
 }
@@ -233,6 +265,32 @@ __device__ __forceinline__ void glu_finish(const Params& p, const uint32_t (&r)[
 }
 
 
+// One accumulator tile through the gated-activation epilogue, for ONE of the two warps that share a TMEM lane
+// quarter: `half` (0 / 1) takes the even / odd 32-column chunks.  Two register buffers: the operands of the
+// warp's next chunk are in flight while the current one is computed (q0 arrives pre-loaded with the first).
+template <int BLOCK_N>
+__device__ __forceinline__ void glu_epilogue_tile(const Params& p, uint32_t tmem_tile, GluRegs& q0, int row,
+                                                  bool row_ok, bool has_k, int col_tile, int half) {
+  GluRegs q1;
+#pragma unroll 1
+  for (int c = 32 * half; c < BLOCK_N; c += 128) {
+    const int colA = col_tile + c, colB = colA + 64, colC = colA + 128;
+    if (colA >= p.N) break;                                   // warp-uniform
+    const bool hasB = (c + 64 < BLOCK_N) && colB < p.N;
+    const bool hasC = (c + 128 < BLOCK_N) && colC < p.N;
+    uint32_t r[32];
+    if (row_ok && hasB) glu_prefetch(p, q1, row, colB);
+    tmem_ld32(tmem_tile + (uint32_t)c, r);
+    tmem_ld_wait(r);
+    if (row_ok) glu_finish(p, r, q0, has_k, row, colA);
+    if (!hasB) break;
+    if (row_ok && hasC) glu_prefetch(p, q0, row, colC);
+    tmem_ld32(tmem_tile + (uint32_t)(c + 64), r);
+    tmem_ld_wait(r);
+    if (row_ok) glu_finish(p, r, q1, has_k, row, colB);
+  }
+}
+
 template <int BLOCK_N>
 struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
@@ -244,7 +302,7 @@ struct Cfg {
 };
 
 template <int BLOCK_N, int EPI = 0>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(threads_of(EPI), 1)
 gemm_kernel(const __grid_constant__ Params p) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -275,7 +333,7 @@ gemm_kernel(const __grid_constant__ Params p) {
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI ? 8 : 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -391,24 +449,26 @@ gemm_kernel(const __grid_constant__ Params p) {
       work_range(w, tile, kb0, kb1);
       tile_coords(tile, m_blk, n_blk);
       const int sp = w / num_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int row = m_blk * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       const bool has_k = kb1 > kb0;
+      GluRegs gq0;
+      if constexpr (EPI) {                         // first chunk's operands fly while the tile's MMAs finish
+        const int colp = n_blk * BLOCK_N + 32 * ((warp - 2) >> 2);
+        if (row_ok && colp < p.N) glu_prefetch(p, gq0, row, colp);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if constexpr (EPI) {
+        glu_epilogue_tile<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), gq0,
+                                   row, row_ok, has_k, n_blk * BLOCK_N, (warp - 2) >> 2);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        const int col0 = n_blk * BLOCK_N + c;
-        if (col0 >= p.N) break;                   // warp-uniform
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
-        if constexpr (EPI) {
-          GluRegs gq;
-          if (row_ok) glu_prefetch(p, gq, row, col0);
-          tmem_ld32(taddr, r);
-          tmem_ld_wait(r);
-          if (row_ok) glu_finish(p, r, gq, has_k, row, col0);
-        } else {
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          const int col0 = n_blk * BLOCK_N + c;
+          if (col0 >= p.N) break;                   // warp-uniform
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
           tmem_ld32(taddr, r);
           tmem_ld_wait(r);
           if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
@@ -451,7 +511,7 @@ struct Cfg2 {
 };
 
 template <int BLOCK_N, int EPI = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_of(EPI), 1)
 gemm2_kernel(const __grid_constant__ Params p) {
   using C = Cfg2<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -486,7 +546,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
       // full: leader's own arrive.expect_tx + the peer producer's remote arrive
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
       // tmem_empty (leader's copy is the one used): 4 epilogue warps x 2 CTAs
-      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI ? 16 : 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -604,24 +664,26 @@ gemm2_kernel(const __grid_constant__ Params p) {
       work_range(w, tile, kb0, kb1);
       tile_coords(tile, m_pair, n_blk);
       const int sp = w / num_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       const bool has_k = kb1 > kb0;
+      GluRegs gq0;
+      if constexpr (EPI) {                         // first chunk's operands fly while the tile's MMAs finish
+        const int colp = n_blk * BLOCK_N + 32 * ((warp - 2) >> 2);
+        if (row_ok && colp < p.N) glu_prefetch(p, gq0, row, colp);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if constexpr (EPI) {
+        glu_epilogue_tile<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), gq0,
+                                   row, row_ok, has_k, n_blk * BLOCK_N, (warp - 2) >> 2);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        const int col0 = n_blk * BLOCK_N + c;
-        if (col0 >= p.N) break;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
-        if constexpr (EPI) {
-          GluRegs gq;
-          if (row_ok) glu_prefetch(p, gq, row, col0);
-          tmem_ld32(taddr, r);
-          tmem_ld_wait(r);
-          if (row_ok) glu_finish(p, r, gq, has_k, row, col0);
-        } else {
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          const int col0 = n_blk * BLOCK_N + c;
+          if (col0 >= p.N) break;
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
           tmem_ld32(taddr, r);
           tmem_ld_wait(r);
           if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
@@ -681,7 +743,7 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  gemm_kernel<BLOCK_N, EPI><<<grid, threads_of(EPI), C::SMEM_BYTES, st>>>(p);
   return UB200_OK;
 }
 
@@ -695,7 +757,7 @@ static int launch2(const Params& p, int grid, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm2_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);   // __cluster_dims__(2,1,1)
+  gemm2_kernel<BLOCK_N, EPI><<<grid, threads_of(EPI), C::SMEM_BYTES, st>>>(p);   // __cluster_dims__(2,1,1)
   return UB200_OK;
 }
 
@@ -838,9 +900,9 @@ extern "C" int ub200_gemm_glu(int mode, int act, int M, int N, const ub200_gemm_
     return UB200_ERR_BAD_ARG;
   if (dtype != UB200_BF16 && dtype != UB200_F16) return UB200_ERR_BAD_ARG;
   if (!C || !e || !g) return UB200_ERR_BAD_ARG;
-  // the epilogue moves 16-byte vectors of 32-column chunks: every row of C / e / g must start 16-byte aligned
-  if ((reinterpret_cast<uintptr_t>(C) & 15) || (reinterpret_cast<uintptr_t>(e) & 15) ||
-      (reinterpret_cast<uintptr_t>(g) & 15) || (ldc % 8) || (ld_eg % 8) || ldc < N || ld_eg < N)
+  // the epilogue moves 32-byte vectors of 32-column chunks: every row of C / e / g must start 32-byte aligned
+  if ((reinterpret_cast<uintptr_t>(C) & 31) || (reinterpret_cast<uintptr_t>(e) & 31) ||
+      (reinterpret_cast<uintptr_t>(g) & 31) || (ldc % 16) || (ld_eg % 16) || ldc < N || ld_eg < N)
     return UB200_ERR_BAD_ARG;
   if (N % 32) return UB200_ERR_UNSUPPORTED;   // whole 32-column chunks only (the caller falls back to two launches)
   ub::gemm::GluArgs ga{mode, act, e, g, ld_eg};

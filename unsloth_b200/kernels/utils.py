@@ -252,7 +252,7 @@ def glu_fusable(N, *tensors) -> bool:
         return False
     for t in tensors:
         if t.dtype not in (torch.bfloat16, torch.float16) or t.dim() != 2 or t.stride(1) != 1 \
-                or t.stride(0) % 8 or t.data_ptr() % 16:
+                or t.stride(0) % 16 or t.data_ptr() % 32:
             return False
     return True
 
