@@ -31,6 +31,9 @@ def timed(fn):
 
 
 def main():
+    act = int(sys.argv[1]) if len(sys.argv) > 1 else 0          # 0 SwiGLU, 1 GEGLU-tanh, 2 GEGLU-erf
+    two_fwd = [K.swiglu_fg_kernel, K.geglu_approx_forward_kernel, K.geglu_exact_forward_kernel][act]
+    two_bwd = [K.swiglu_DWf_DW_dfg_kernel, K.geglu_approx_backward_kernel, K.geglu_exact_backward_kernel][act]
     torch.manual_seed(0)
     KU.set_keep_dequant(True)
     T_, H, I, r = 8192, 4096, 14336, 16
@@ -52,19 +55,19 @@ def main():
 
     def bwd_two():
         KU.gemm(T_, I, bsegs, out, b_mn=True)
-        K.swiglu_DWf_DW_dfg_kernel(out, e, g)
+        two_bwd(out, e, g)
 
     def fwd_two():
         KU.gemm(T_, I, fsegs, out)
-        K.swiglu_fg_kernel(e, out)
+        two_fwd(e.view(1, T_, I), out.view(1, T_, I))
 
     variants = {
         "bwd: DW gemm alone": lambda: KU.gemm(T_, I, bsegs, out, b_mn=True),
         "bwd: DW gemm + glu_bwd (2 launches)": bwd_two,
-        "bwd: gemm_glu (1 launch)": lambda: KU.gemm_glu(L.GLU_EPI_BWD, 0, T_, I, bsegs, out, e, g, b_mn=True),
+        "bwd: gemm_glu (1 launch)": lambda: KU.gemm_glu(L.GLU_EPI_BWD, act, T_, I, bsegs, out, e, g, b_mn=True),
         "fwd: up gemm alone": lambda: KU.gemm(T_, I, fsegs, out),
         "fwd: up gemm + glu_fwd (2 launches)": fwd_two,
-        "fwd: gemm_glu (1 launch)": lambda: KU.gemm_glu(L.GLU_EPI_FWD, 0, T_, I, fsegs, out2, e, out),
+        "fwd: gemm_glu (1 launch)": lambda: KU.gemm_glu(L.GLU_EPI_FWD, act, T_, I, fsegs, out2, e, out),
     }
     ts = {k: [] for k in variants}
     for rnd in range(11):
@@ -74,7 +77,7 @@ def main():
                 ts[k].append(t)
             e.normal_(); g.normal_()          # in-place outputs drift otherwise
     for k in variants:
-        print(json.dumps({"variant": k, "ms": round(med(ts[k]), 4)}), flush=True)
+        print(json.dumps({"act": act, "variant": k, "ms": round(med(ts[k]), 4)}), flush=True)
 
 
 if __name__ == "__main__":

@@ -203,7 +203,7 @@ int ub200_gemm_workspace_bytes(int M, int N, int split_k, int64_t* bytes);
  * accumulator tile is rounded to `dtype` exactly where the reference's matmul output is, then the
  * per-element code of ub200_glu_fwd / ub200_glu_bwd runs on it in registers (same bits as the
  * two-launch form).  Operand conventions as ub200_gemm; no split-K, no accumulate; `dtype` (bf16 /
- * fp16) is the operand AND output dtype; C, e, g 32-byte aligned, ldc and ld_eg multiples of 16, N a multiple of 32 (else UB200_ERR_UNSUPPORTED).
+ * fp16) is the operand AND output dtype; C, e, g 32-byte aligned, ldc and ld_eg multiples of 16, N a multiple of the tile width (block_n, auto: 256 / 128 / 64 as for ub200_gemm) and alpha == 1, else UB200_ERR_UNSUPPORTED.
  *   mode UB200_GLU_EPI_FWD: acc = up projection.   g <- acc,  C <- act(e).to(dtype) * g   (e read only:
  *                           the gate projection written by the previous launch)
  *   mode UB200_GLU_EPI_BWD: acc = DW = dY @ W_down (+ LoRA).  C <- h = f(e) * g,  e <- df = DW * f,

@@ -171,7 +171,8 @@ def gemm(M, N, segs, n_segs, a_mn, b_mn, abdt, C, ldc, cdt, alpha, accumulate, s
 def gemm_glu(mode, act, M, N, segs, n_segs, a_mn, b_mn, dt, C, ldc, e, g, ld_eg, alpha, block_n, cta_group,
              stream):
     """ub200_gemm_glu: the GEMM, rounded to `dt`, then the gated activation on the tile (header contract)."""
-    assert mode in (1, 2) and N % 32 == 0 and ldc % 16 == 0 and ld_eg % 16 == 0 and dt in (1, 2)
+    bn = block_n or (256 if N > 128 else (128 if N > 64 else 64))
+    assert mode in (1, 2) and N % bn == 0 and alpha == 1.0 and ldc % 16 == 0 and ld_eg % 16 == 0 and dt in (1, 2)
     d = _DT[dt]
     tile = torch.empty(M, N, dtype=d)
     gemm(M, N, segs, n_segs, a_mn, b_mn, dt, tile.data_ptr(), N, dt, alpha, 0, 1, None, block_n, cta_group,

@@ -31,9 +31,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 x 2 B = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
-// kernels with the gated-activation epilogue run EIGHT epilogue warps (two per TMEM lane quarter, interleaved
-// 32-column chunks): the epilogue streams 3-5x the bytes of a plain store and is latency-bound with four
-constexpr int NUM_THREADS_GLU = 320;
+// kernels with the gated-activation epilogue run SIXTEEN epilogue warps (four per TMEM lane quarter, interleaved
+// 16-column units): the epilogue does ~37 instructions per element on 3-5x the bytes of a plain store, and with
+// four warps (one per scheduler) it was latency-bound at 1.6x the tile's MMA time (profiles/r2_glu_epilogue_ncu.txt)
+constexpr int GLU_WARPS_PER_QUARTER = 4;
+constexpr int NUM_THREADS_GLU = 64 + 128 * GLU_WARPS_PER_QUARTER;
 __host__ __device__ constexpr int threads_of(int epi) { return epi ? NUM_THREADS_GLU : NUM_THREADS; }
 constexpr int MAX_SEGS = UB200_GEMM_MAX_SEGMENTS;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
@@ -171,12 +173,12 @@ __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&r)
 // stores); they are evict-first, the operand tiles of the main loop own the L2.
 // ---------------------------------------------------------------------------------------
 struct GluRegs {
-  uint32_t e[16];     // 32 consecutive 16-bit values of this thread's row
-  uint32_t g[16];
+  uint32_t e[8];      // 16 consecutive 16-bit values of this thread's row (one 32-byte sector)
+  uint32_t g[8];
 };
 
 // 32-byte global accesses (sm_100: LDG.E.256 / STG.E.256): one thread moves a whole 32-byte sector per
-// instruction, so a row's 64-byte chunk is 2 requests instead of 4 half-sector ones.  Loads are evict-first.
+// instruction.  Loads are evict-first (the operand tiles of the main loop own the L2).
 __device__ __forceinline__ void ldg256_cs(const void* ptr, uint32_t* r) {
   asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -188,16 +190,11 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* r) {
                : "memory");
 }
 
+// operands of one 16-column unit (row, col0 .. col0 + 15)
 __device__ __forceinline__ void glu_prefetch(const Params& p, GluRegs& q, int row, int col0) {
-  if (col0 + 32 > p.N) return;                                  // never taken: the host requires N % 32 == 0
-  const uint16_t* ep = reinterpret_cast<const uint16_t*>(p.glu_e) + (int64_t)row * p.ld_eg + col0;
-  ldg256_cs(ep, q.e);
-  ldg256_cs(ep + 16, q.e + 8);
-  if (p.glu_mode == UB200_GLU_EPI_BWD) {
-    const uint16_t* gp = reinterpret_cast<const uint16_t*>(p.glu_g) + (int64_t)row * p.ld_eg + col0;
-    ldg256_cs(gp, q.g);
-    ldg256_cs(gp + 16, q.g + 8);
-  }
+  ldg256_cs(reinterpret_cast<const uint16_t*>(p.glu_e) + (int64_t)row * p.ld_eg + col0, q.e);
+  if (p.glu_mode == UB200_GLU_EPI_BWD)
+    ldg256_cs(reinterpret_cast<const uint16_t*>(p.glu_g) + (int64_t)row * p.ld_eg + col0, q.g);
 }
 
 // element `hi` (0 / 1) of a packed pair of 16-bit values, as fp32 (register-only: no address is taken)
@@ -219,75 +216,78 @@ template <> __device__ __forceinline__ uint32_t pack16<__half>(float lo, float h
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+// one 16-column unit: accumulators r (alpha == 1, checked by the host) + operands q -> 2 or 3 sector stores
 template <typename T, int ACT>
-__device__ __forceinline__ void glu_finish_t(const Params& p, const uint32_t (&r)[32], const GluRegs& q,
-                                             bool has_k, int row, int col0) {
-  T* cp = reinterpret_cast<T*>(p.C) + (int64_t)row * p.ldc + col0;
-  T* ep = reinterpret_cast<T*>(p.glu_e) + (int64_t)row * p.ld_eg + col0;
-  T* gp = reinterpret_cast<T*>(p.glu_g) + (int64_t)row * p.ld_eg + col0;
+__device__ __forceinline__ void glu_finish_t(const Params& p, const uint32_t (&r)[16], const GluRegs& q,
+                                             int row, int col0) {
   const bool bwd = p.glu_mode == UB200_GLU_EPI_BWD;
-  if (col0 + 32 <= p.N) {
+  uint32_t w0[8], w1[8], w2[8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {                    // 16 columns = one 32-byte sector of every tensor
-      uint32_t w0[8], w1[8], w2[8];
+  for (int k = 0; k < 8; ++k) {
+    float o0[2], o1[2], o2[2];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float o0[2], o1[2], o2[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float acc = DT<T>::rnd(has_k ? __uint_as_float(r[16 * i + 2 * k + j]) * p.alpha : 0.f);
-          const float ek = unpack16<T>(q.e[8 * i + k], j);
-          if (bwd) glu_bwd_elem<T, ACT>(acc, ek, unpack16<T>(q.g[8 * i + k], j), o0[j], o1[j], o2[j]);
-          else { o0[j] = glu_fwd_elem<T, ACT>(ek, acc); o1[j] = 0.f; o2[j] = acc; }
-        }
-        w0[k] = pack16<T>(o0[0], o0[1]);
-        w1[k] = pack16<T>(o1[0], o1[1]);
-        w2[k] = pack16<T>(o2[0], o2[1]);
-      }
-      stg256(cp + 16 * i, w0);                       // h
-      if (bwd) stg256(ep + 16 * i, w1);              // df (in place over e)
-      stg256(gp + 16 * i, w2);                       // de (in place over g) / g
+    for (int j = 0; j < 2; ++j) {
+      const float acc = DT<T>::rnd(__uint_as_float(r[2 * k + j]));
+      const float ek = unpack16<T>(q.e[k], j);
+      if (bwd) glu_bwd_elem<T, ACT>(acc, ek, unpack16<T>(q.g[k], j), o0[j], o1[j], o2[j]);
+      else { o0[j] = glu_fwd_elem<T, ACT>(ek, acc); o1[j] = 0.f; o2[j] = acc; }
     }
+    w0[k] = pack16<T>(o0[0], o0[1]);
+    w1[k] = pack16<T>(o1[0], o1[1]);
+    w2[k] = pack16<T>(o2[0], o2[1]);
   }
+  stg256(reinterpret_cast<T*>(p.C) + (int64_t)row * p.ldc + col0, w0);                      // h
+  if (bwd) stg256(reinterpret_cast<T*>(p.glu_e) + (int64_t)row * p.ld_eg + col0, w1);       // df (over e)
+  stg256(reinterpret_cast<T*>(p.glu_g) + (int64_t)row * p.ld_eg + col0, w2);                // de (over g) / g
 }
 
-__device__ __forceinline__ void glu_finish(const Params& p, const uint32_t (&r)[32], const GluRegs& q,
-                                           bool has_k, int row, int col0) {
+__device__ __forceinline__ void glu_finish(const Params& p, const uint32_t (&r)[16], const GluRegs& q, int row,
+                                           int col0) {
   if (p.c_dtype == UB200_BF16) {
-    if (p.glu_act == ACT_SWIGLU) glu_finish_t<__nv_bfloat16, ACT_SWIGLU>(p, r, q, has_k, row, col0);
-    else if (p.glu_act == ACT_GEGLU_APPROX) glu_finish_t<__nv_bfloat16, ACT_GEGLU_APPROX>(p, r, q, has_k, row, col0);
-    else glu_finish_t<__nv_bfloat16, ACT_GEGLU_EXACT>(p, r, q, has_k, row, col0);
+    if (p.glu_act == ACT_SWIGLU) glu_finish_t<__nv_bfloat16, ACT_SWIGLU>(p, r, q, row, col0);
+    else if (p.glu_act == ACT_GEGLU_APPROX) glu_finish_t<__nv_bfloat16, ACT_GEGLU_APPROX>(p, r, q, row, col0);
+    else glu_finish_t<__nv_bfloat16, ACT_GEGLU_EXACT>(p, r, q, row, col0);
   } else {
-    if (p.glu_act == ACT_SWIGLU) glu_finish_t<__half, ACT_SWIGLU>(p, r, q, has_k, row, col0);
-    else if (p.glu_act == ACT_GEGLU_APPROX) glu_finish_t<__half, ACT_GEGLU_APPROX>(p, r, q, has_k, row, col0);
-    else glu_finish_t<__half, ACT_GEGLU_EXACT>(p, r, q, has_k, row, col0);
+    if (p.glu_act == ACT_SWIGLU) glu_finish_t<__half, ACT_SWIGLU>(p, r, q, row, col0);
+    else if (p.glu_act == ACT_GEGLU_APPROX) glu_finish_t<__half, ACT_GEGLU_APPROX>(p, r, q, row, col0);
+    else glu_finish_t<__half, ACT_GEGLU_EXACT>(p, r, q, row, col0);
   }
 }
 
-
-// One accumulator tile through the gated-activation epilogue, for ONE of the two warps that share a TMEM lane
-// quarter: `half` (0 / 1) takes the even / odd 32-column chunks.  Two register buffers: the operands of the
-// warp's next chunk are in flight while the current one is computed (q0 arrives pre-loaded with the first).
+// One accumulator tile through the gated-activation epilogue, for ONE of the GLU_WARPS_PER_QUARTER warps that
+// share a TMEM lane quarter: warp `sub` takes the 16-column units sub, sub + 4, sub + 8, ...  (BLOCK_N / 64 per
+// tile; the host guarantees N % BLOCK_N == 0, so every tile is whole).  Two register buffers: q0 arrives loaded
+// with the tile's first unit; while a unit is computed the operands of the next one are in flight, and during
+// the LAST unit those of the NEXT TILE's first unit (nrow, ncol; nrow < 0: none) -- no load latency is exposed
+// at a tile boundary.
 template <int BLOCK_N>
 __device__ __forceinline__ void glu_epilogue_tile(const Params& p, uint32_t tmem_tile, GluRegs& q0, int row,
-                                                  bool row_ok, bool has_k, int col_tile, int half) {
-  GluRegs q1;
+                                                  bool row_ok, int col_tile, int sub, int nrow, int ncol) {
+  constexpr int UNITS = BLOCK_N / (16 * GLU_WARPS_PER_QUARTER);
+  uint32_t r[16];
+  if constexpr (UNITS == 1) {
+    tmem_ld16(tmem_tile + (uint32_t)(16 * sub), r);
+    tmem_ld_wait16(r);
+    if (row_ok) glu_finish(p, r, q0, row, col_tile + 16 * sub);
+    if (nrow >= 0) glu_prefetch(p, q0, nrow, ncol);
+  } else {
+    GluRegs q1;
 #pragma unroll 1
-  for (int c = 32 * half; c < BLOCK_N; c += 128) {
-    const int colA = col_tile + c, colB = colA + 64, colC = colA + 128;
-    if (colA >= p.N) break;                                   // warp-uniform
-    const bool hasB = (c + 64 < BLOCK_N) && colB < p.N;
-    const bool hasC = (c + 128 < BLOCK_N) && colC < p.N;
-    uint32_t r[32];
-    if (row_ok && hasB) glu_prefetch(p, q1, row, colB);
-    tmem_ld32(tmem_tile + (uint32_t)c, r);
-    tmem_ld_wait(r);
-    if (row_ok) glu_finish(p, r, q0, has_k, row, colA);
-    if (!hasB) break;
-    if (row_ok && hasC) glu_prefetch(p, q0, row, colC);
-    tmem_ld32(tmem_tile + (uint32_t)(c + 64), r);
-    tmem_ld_wait(r);
-    if (row_ok) glu_finish(p, r, q1, has_k, row, colB);
+    for (int j = 0; j < UNITS; j += 2) {
+      const int cA = 16 * sub + 64 * j, cB = cA + 64;
+      if (row_ok) glu_prefetch(p, q1, row, col_tile + cB);
+      tmem_ld16(tmem_tile + (uint32_t)cA, r);
+      tmem_ld_wait16(r);
+      if (row_ok) glu_finish(p, r, q0, row, col_tile + cA);
+      if (j + 2 < UNITS) {
+        if (row_ok) glu_prefetch(p, q0, row, col_tile + cB + 64);
+      } else if (nrow >= 0) {
+        glu_prefetch(p, q0, nrow, ncol);
+      }
+      tmem_ld16(tmem_tile + (uint32_t)cB, r);
+      tmem_ld_wait16(r);
+      if (row_ok) glu_finish(p, r, q1, row, col_tile + cB);
+    }
   }
 }
 
@@ -333,7 +333,7 @@ gemm_kernel(const __grid_constant__ Params p) {
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI ? 8 : 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI ? 4 * GLU_WARPS_PER_QUARTER : 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -444,25 +444,50 @@ gemm_kernel(const __grid_constant__ Params p) {
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      int tile, kb0, kb1, m_blk, n_blk;
-      work_range(w, tile, kb0, kb1);
-      tile_coords(tile, m_blk, n_blk);
-      const int sp = w / num_tiles;
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool has_k = kb1 > kb0;
+    if constexpr (EPI) {
+      // gated-activation epilogue: GLU_WARPS_PER_QUARTER warps per lane quarter, see glu_epilogue_tile
+      const int sub = (warp - 2) >> 2;
+      auto coords = [&](int w, int& row, int& col_tile) {
+        int tile, kb0, kb1, m_blk, n_blk;
+        work_range(w, tile, kb0, kb1);
+        tile_coords(tile, m_blk, n_blk);
+        row = m_blk * BLOCK_M + q * 32 + lane;
+        col_tile = n_blk * BLOCK_N;
+      };
       GluRegs gq0;
-      if constexpr (EPI) {                         // first chunk's operands fly while the tile's MMAs finish
-        const int colp = n_blk * BLOCK_N + 32 * ((warp - 2) >> 2);
-        if (row_ok && colp < p.N) glu_prefetch(p, gq0, row, colp);
+      int row, col_tile;
+      if ((int)blockIdx.x < num_work) {
+        coords(blockIdx.x, row, col_tile);
+        if (row < p.M) glu_prefetch(p, gq0, row, col_tile + 16 * sub);
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      if constexpr (EPI) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        coords(w, row, col_tile);
+        int nrow = -1, ncol = 0;
+        if (w + (int)gridDim.x < num_work) {
+          int nr, nc;
+          coords(w + gridDim.x, nr, nc);
+          if (nr < p.M) { nrow = nr; ncol = nc + 16 * sub; }
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
         glu_epilogue_tile<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), gq0,
-                                   row, row_ok, has_k, n_blk * BLOCK_N, (warp - 2) >> 2);
-      } else {
+                                   row, row < p.M, col_tile, sub, nrow, ncol);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int tile, kb0, kb1, m_blk, n_blk;
+        work_range(w, tile, kb0, kb1);
+        tile_coords(tile, m_blk, n_blk);
+        const int sp = w / num_tiles;
+        const int row = m_blk * BLOCK_M + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        const bool has_k = kb1 > kb0;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
           const int col0 = n_blk * BLOCK_N + c;
@@ -473,12 +498,12 @@ gemm_kernel(const __grid_constant__ Params p) {
           tmem_ld_wait(r);
           if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
         }
+        // release the accumulator buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      // release the accumulator buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -546,7 +571,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
       // full: leader's own arrive.expect_tx + the peer producer's remote arrive
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
       // tmem_empty (leader's copy is the one used): 4 epilogue warps x 2 CTAs
-      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI ? 16 : 8); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI ? 8 * GLU_WARPS_PER_QUARTER : 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -659,25 +684,49 @@ gemm2_kernel(const __grid_constant__ Params p) {
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = pair; w < num_work; w += num_pairs) {
-      int tile, kb0, kb1, m_pair, n_blk;
-      work_range(w, tile, kb0, kb1);
-      tile_coords(tile, m_pair, n_blk);
-      const int sp = w / num_tiles;
-      const int row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool has_k = kb1 > kb0;
+    if constexpr (EPI) {
+      const int sub = (warp - 2) >> 2;
+      auto coords = [&](int w, int& row, int& col_tile) {
+        int tile, kb0, kb1, m_pair, n_blk;
+        work_range(w, tile, kb0, kb1);
+        tile_coords(tile, m_pair, n_blk);
+        row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
+        col_tile = n_blk * BLOCK_N;
+      };
       GluRegs gq0;
-      if constexpr (EPI) {                         // first chunk's operands fly while the tile's MMAs finish
-        const int colp = n_blk * BLOCK_N + 32 * ((warp - 2) >> 2);
-        if (row_ok && colp < p.N) glu_prefetch(p, gq0, row, colp);
+      int row, col_tile;
+      if (pair < num_work) {
+        coords(pair, row, col_tile);
+        if (row < p.M) glu_prefetch(p, gq0, row, col_tile + 16 * sub);
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      if constexpr (EPI) {
+      for (int w = pair; w < num_work; w += num_pairs) {
+        coords(w, row, col_tile);
+        int nrow = -1, ncol = 0;
+        if (w + num_pairs < num_work) {
+          int nr, nc;
+          coords(w + num_pairs, nr, nc);
+          if (nr < p.M) { nrow = nr; ncol = nc + 16 * sub; }
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
         glu_epilogue_tile<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), gq0,
-                                   row, row_ok, has_k, n_blk * BLOCK_N, (warp - 2) >> 2);
-      } else {
+                                   row, row < p.M, col_tile, sub, nrow, ncol);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0u);   // leader's barrier
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else {
+      for (int w = pair; w < num_work; w += num_pairs) {
+        int tile, kb0, kb1, m_pair, n_blk;
+        work_range(w, tile, kb0, kb1);
+        tile_coords(tile, m_pair, n_blk);
+        const int sp = w / num_tiles;
+        const int row = m_pair * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        const bool has_k = kb1 > kb0;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
           const int col0 = n_blk * BLOCK_N + c;
@@ -688,11 +737,11 @@ gemm2_kernel(const __grid_constant__ Params p) {
           tmem_ld_wait(r);
           if (row_ok) store_chunk(p, r, has_k, row, col0, sp);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0u);   // leader's barrier
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tempty_bar(acc), 0u);   // leader's barrier
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -904,7 +953,13 @@ extern "C" int ub200_gemm_glu(int mode, int act, int M, int N, const ub200_gemm_
   if ((reinterpret_cast<uintptr_t>(C) & 31) || (reinterpret_cast<uintptr_t>(e) & 31) ||
       (reinterpret_cast<uintptr_t>(g) & 31) || (ldc % 16) || (ld_eg % 16) || ldc < N || ld_eg < N)
     return UB200_ERR_BAD_ARG;
-  if (N % 32) return UB200_ERR_UNSUPPORTED;   // whole 32-column chunks only (the caller falls back to two launches)
+  // whole tiles only and no scaling (the caller falls back to two launches otherwise)
+  {
+    int bn = block_n;
+    if (bn == 0) bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    if (bn != 256 && bn != 128 && bn != 64) return UB200_ERR_BAD_ARG;
+    if (N % bn || alpha != 1.0f) return UB200_ERR_UNSUPPORTED;
+  }
   ub::gemm::GluArgs ga{mode, act, e, g, ld_eg};
   return gemm_impl(M, N, segs, n_segs, a_mn_major, b_mn_major, dtype, C, ldc, dtype, alpha, 0, 1, nullptr,
                    block_n, cta_group, &ga, stream);

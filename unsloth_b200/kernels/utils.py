@@ -247,8 +247,8 @@ def fused_glu_enabled(direction) -> bool:
 
 
 def glu_fusable(N, *tensors) -> bool:
-    """Conditions of ub200_gemm_glu: 16-bit row-major [T, N] tensors, whole 32-column chunks."""
-    if N % 32:
+    """Conditions of ub200_gemm_glu: 16-bit row-major [T, N] tensors with 32-byte aligned rows, whole tiles."""
+    if N % (256 if N > 128 else (128 if N > 64 else 64)):
         return False
     for t in tensors:
         if t.dtype not in (torch.bfloat16, torch.float16) or t.dim() != 2 or t.stride(1) != 1 \
