@@ -529,6 +529,28 @@ def test_cast_pad_multi_and_accumulate_multi_match_the_single_tensor_forms():
     L.call("ub200_cast_pad_multi", arr, n, L.stream())
     for a, b in zip(dsts, refs):
         assert torch.equal(a, b)
+    # the 16-byte-store path of the batched kernel: the shapes a LoRA step really casts (rank blocks padded to
+    # 64, 16-bit destinations with 8-column granularity), against the single-tensor form
+    cases = [((16, 4096), (64, 4096), 16, 0, False), ((16, 14336), (64, 14336), 0, 0, False),
+             ((14336, 16), (14336, 64), 0, 32, False), ((1024, 16), (64, 1024), 16, 0, True),
+             ((4096, 16), (4096, 64), 0, 0, False), ((24, 520), (40, 528), 8, 8, False)]
+    m = len(cases) * 2
+    arr2, keep = (L.CastDesc * m)(), []
+    for i in range(m):
+        (r, c), dshape, ro, co, tr = cases[i % len(cases)]
+        dt = [torch.bfloat16, torch.float16][i // len(cases)]
+        src = torch.randn(r, c, device=DEV)
+        dst = torch.full(dshape, 7.0, dtype=dt, device=DEV)
+        ref = torch.full_like(dst, 7.0)
+        cast_pad(src, ref, ro, co, 1.5 + i, tr)
+        d = arr2[i]
+        d.src, d.dst, d.src_ld, d.dst_ld = src.data_ptr(), dst.data_ptr(), src.stride(0), dst.stride(0)
+        d.src_dtype, d.dst_dtype, d.rows, d.cols = L.dt(src), L.dt(dst), r, c
+        d.dst_rows, d.dst_cols, d.row_off, d.col_off, d.scale, d.transpose = dshape[0], dshape[1], ro, co, 1.5 + i, int(tr)
+        keep.append((src, dst, ref))
+    L.call("ub200_cast_pad_multi", arr2, m, L.stream())
+    for _, a, b in keep:
+        assert torch.equal(a, b)
     acc = (L.AccDesc * n)()
     gs, views, exp = [], [], []
     for i in range(n):

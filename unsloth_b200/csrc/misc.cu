@@ -71,21 +71,55 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 // (a chunk of 40 per launch, < 4 KB), so nothing has to be staged on the device and the launches
 // are CUDA-graph capturable; blockIdx.y = descriptor, blockIdx.x strides over its elements.
 constexpr int MULTI_CHUNK = 40;
-constexpr int MULTI_CTAS = 8;
+// CTAs per descriptor.  8 (first cut) left the batched casts at ~40 G elements/s -- 3.7 ms of a cfg2 step for
+// 0.45 GB of traffic (profiles/r2_launches_bench_full_summary.txt): 2048 threads per descriptor, a 64-bit
+// division and a 2-byte store per element.  Now 32 CTAs, 32-bit index arithmetic and, where the destination
+// allows it (16-bit, 8-column granularity), one 16-byte store per thread per iteration.
+constexpr int MULTI_CTAS = 32;
 struct CastBatch { ub200_cast_desc d[MULTI_CHUNK]; };
 struct AccBatch { ub200_acc_desc d[MULTI_CHUNK]; };
+
+// value of destination element (dr, dc): scale * src at the placed block, zero in the padding
+__device__ __forceinline__ float cast_pad_value(const ub200_cast_desc& d, int dr, int dc) {
+  const int lr = dr - d.row_off, lc = dc - d.col_off;
+  const int sr = d.transpose ? lc : lr, sc = d.transpose ? lr : lc;
+  if (sr >= 0 && sc >= 0 && sr < d.rows && sc < d.cols)
+    return d.scale * load_as_f(d.src, d.src_dtype, (int64_t)sr * d.src_ld + sc);
+  return 0.f;
+}
 
 __global__ void __launch_bounds__(256) cast_pad_multi_kernel(const __grid_constant__ CastBatch b) {
   const ub200_cast_desc& d = b.d[blockIdx.y];
   const int64_t total = (int64_t)d.dst_rows * d.dst_cols;
+  const bool vec = d.dst_dtype != UB200_F32 && (d.dst_cols % 8) == 0 && (d.dst_ld % 8) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d.dst) & 15) == 0 && total < (1ll << 31);
+  if (vec) {
+    const uint32_t cv = (uint32_t)d.dst_cols / 8u, nv = (uint32_t)(total / 8);
+    const bool bf = d.dst_dtype == UB200_BF16;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+      const uint32_t dr = i / cv, dc0 = (i - dr * cv) * 8u;
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = cast_pad_value(d, (int)dr, (int)dc0 + 2 * k);
+        const float hi = cast_pad_value(d, (int)dr, (int)dc0 + 2 * k + 1);
+        if (bf) {
+          const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+          w[k] = *reinterpret_cast<const uint32_t*>(&t);
+        } else {
+          const __half2 t = __floats2half2_rn(lo, hi);
+          w[k] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(d.dst) + (int64_t)dr * d.dst_ld + dc0) =
+          make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int dr = (int)(i / d.dst_cols), dc = (int)(i - (int64_t)dr * d.dst_cols);
-    const int lr = dr - d.row_off, lc = dc - d.col_off;
-    const int sr = d.transpose ? lc : lr, sc = d.transpose ? lr : lc;
-    float v = 0.f;
-    if (sr >= 0 && sc >= 0 && sr < d.rows && sc < d.cols)
-      v = d.scale * load_as_f(d.src, d.src_dtype, (int64_t)sr * d.src_ld + sc);
+    const float v = cast_pad_value(d, dr, dc);
     const int64_t o = (int64_t)dr * d.dst_ld + dc;
     if (d.dst_dtype == UB200_BF16) reinterpret_cast<__nv_bfloat16*>(d.dst)[o] = __float2bfloat16_rn(v);
     else if (d.dst_dtype == UB200_F16) reinterpret_cast<__half*>(d.dst)[o] = __float2half_rn(v);
@@ -94,19 +128,24 @@ __global__ void __launch_bounds__(256) cast_pad_multi_kernel(const __grid_consta
 }
 
 // dst[r, c] (contiguous fp32) += src[r * src_rs + c * src_cs]
+template <typename I>
+__device__ __forceinline__ void accumulate_one(const ub200_acc_desc& d, I total) {
+  // walk the SOURCE's fast axis with consecutive threads when it is the transposed one
+  const bool src_row_fast = d.src_rs == 1 && d.src_cs != 1;
+  const I rows = (I)d.rows, cols = (I)d.cols;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    I r, c;
+    if (src_row_fast) { c = i / rows; r = i - c * rows; }
+    else { r = i / cols; c = i - r * cols; }
+    d.dst[(int64_t)r * d.cols + (int64_t)c] += d.src[(int64_t)r * d.src_rs + (int64_t)c * d.src_cs];
+  }
+}
+
 __global__ void __launch_bounds__(256) accumulate_multi_kernel(const __grid_constant__ AccBatch b) {
   const ub200_acc_desc& d = b.d[blockIdx.y];
   const int64_t total = (int64_t)d.rows * d.cols;
-  // walk the SOURCE's fast axis with consecutive threads when it is the transposed one
-  const bool src_row_fast = d.src_rs == 1 && d.src_cs != 1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int r, c;
-    if (src_row_fast) { c = (int)(i / d.rows); r = (int)(i - (int64_t)c * d.rows); }
-    else { r = (int)(i / d.cols); c = (int)(i - (int64_t)r * d.cols); }
-    const int64_t o = (int64_t)r * d.cols + c;
-    d.dst[o] += d.src[(int64_t)r * d.src_rs + (int64_t)c * d.src_cs];
-  }
+  if (total < (1ll << 31)) accumulate_one<uint32_t>(d, (uint32_t)total);
+  else accumulate_one<int64_t>(d, total);
 }
 
 }  // namespace ub
