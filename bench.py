@@ -372,7 +372,11 @@ def run_ours(args):
         # over the summed CUDA-event durations of that kernel's launches
         names = {"grouped": "ub::gemm::grouped::gemm_grouped_kernel (persistent tcgen05 cta_group::2; dense GEMMs + "
                             "rank-block producers + split-K dA/dB of a LoRA phase in one launch)",
-                 "gemm2": "ub::gemm::gemm2_kernel (tcgen05 cta_group::2 multi-segment GEMM: lm_head / fused-CE chunks)",
+                 "gemm2": "ub::gemm::gemm2_kernel<256, 0> (tcgen05 cta_group::2 multi-segment GEMM: q/k/v forward, gate, down, "
+                          "MLP dX, lm_head / fused-CE chunks)",
+                 "gemm2_glu": "ub::gemm::gemm2_kernel<256, 1> (the same GEMM with the gated activation in its epilogue: up "
+                              "projection -> g, h; DW -> h, df, de in place; 16 epilogue warps)",
+                 "gemm1_glu": "ub::gemm::gemm_kernel<*, 1> (single-CTA GEMM with the gated-activation epilogue)",
                  "gemm1": "ub::gemm::gemm_kernel (single-CTA tcgen05 GEMM: tails / small problems)"}
         agg = {}
         for (fl, s_, e_, info) in gemm_events:

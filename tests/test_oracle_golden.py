@@ -1,6 +1,8 @@
 """Pins oracle/restate.py (the CPU oracle) against the committed golden vectors that
 oracle/make_golden.py produced by executing the REFERENCE's own Triton kernels
 (TRITON_INTERPRET=1, fp32).  Tolerance: 1e-5 (north_star fp32 gate)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -319,3 +321,34 @@ def test_attention_oracle_vs_torch_sdpa_and_hf_masks():
     Oa, _ = R.attention(Q[:1, :10], K[:1, :10], V[:1, :10], D ** -0.5)
     Ob, _ = R.attention(Q[:1, 10:], K[:1, 10:], V[:1, 10:], D ** -0.5)
     torch.testing.assert_close(Op, torch.cat([Oa, Ob], 1), rtol=1e-5, atol=1e-5)
+
+
+def test_nf4_code_book_is_the_published_normal_float_construction():
+    """bitsandbytes is absent, so the 16 NF4 levels hard-coded in oracle/restate.py, unsloth_b200/nf4.py and
+    csrc/nf4.cu cannot be read off its kernels.  They CAN be re-derived: NF4 is defined (QLoRA, Dettmers et al.
+    2023, appendix E; bitsandbytes.functional.create_normal_map(offset=0.9677083, use_extra_value=True)) as the
+    normalised quantiles of N(0, 1) -- 8 levels on the positive side, 7 on the negative side, plus an exact
+    zero.  Evaluating that construction with scipy reproduces the table BIT FOR BIT in fp32, which pins the
+    table independently of our own transcription; the same check for the 256-entry dynamic map
+    (create_dynamic_map, the second-level code of double quantisation) pins its end points and symmetry."""
+    from scipy.stats import norm
+    offset = 0.9677083
+    pos = norm.ppf(torch.linspace(offset, 0.5, 9)[:-1]).tolist()
+    neg = (-norm.ppf(torch.linspace(offset, 0.5, 8)[:-1])).tolist()
+    v = torch.tensor(pos + [0.0] + neg, dtype=torch.float32).sort().values
+    v = v / v.max()
+    assert torch.equal(v, R.NF4_CODE)
+    from unsloth_b200 import nf4 as product_nf4
+    table = getattr(product_nf4, "NF4_CODE", None)
+    if table is not None:
+        assert torch.equal(torch.as_tensor(table, dtype=torch.float32).cpu(), R.NF4_CODE)
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "unsloth_b200", "csrc",
+                            "nf4.cu")).read()
+    for x in R.NF4_CODE.tolist():
+        if x not in (0.0, 1.0, -1.0):
+            assert repr(abs(x))[:12] in src, x        # the kernel's constant table holds the same literals
+    code = R.create_dynamic_map()
+    assert code.numel() == 256 and torch.equal(code, code.sort().values)
+    assert code[-1] == 1.0 and (code == 0).sum() == 1 and abs(code[0].item() + 0.9929687380790710) < 1e-7
+    # symmetric but for the extra +1.0: every negative level has its positive mirror image
+    assert torch.allclose(-code[code < 0].flip(0), code[code > 0][:-1], rtol=0, atol=0)

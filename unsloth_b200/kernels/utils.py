@@ -286,7 +286,7 @@ def gemm_glu(mode, act, M, N, segs, out, e, g, a_mn=False, b_mn=False, alpha=1.0
         bn = block_n or (256 if N > 128 else (128 if N > 64 else 64))
         pair = cta_group == 2 or (cta_group == 0 and bn >= 128 and M > 128)
         ev.append((2.0 * M * N * sum(sg[3] if len(sg) > 3 else sg[2] for sg in segs), e0, e1,
-                   {"kernel": "gemm2" if pair else "gemm1", "epilogue": "glu"}))
+                   {"kernel": "gemm2_glu" if pair else "gemm1_glu"}))
     return out
 
 
