@@ -732,3 +732,24 @@ def test_glu_epilogue_schedule_matches_two_launch_schedule(cpu_model, emu, monke
     for flag in ("0", "fwd", "bwd"):
         assert torch.equal(res["1"][0], res[flag][0])
         torch.testing.assert_close(res["1"][1], res[flag][1], rtol=0, atol=0)
+
+
+def test_glu_epilogue_falls_back_when_the_kernel_cannot_take_the_shape(cpu_model, emu, monkeypatch):
+    """ub200_gemm_glu needs 16-bit tensors and whole tiles (N % 64 == 0 for N <= 64, % 128 up to 128, % 256
+    above).  An intermediate size of 96, and an fp32 model, must take the two-launch route on their own -- same
+    numbers as with the epilogues switched off, no fused call issued."""
+    P = cpu_model
+    ids = torch.randint(0, TINY["vocab_size"], (1, 10), generator=torch.Generator().manual_seed(4))
+    for dtype, extra in ((torch.bfloat16, {"intermediate_size": 96}), (torch.float32, {})):
+        res = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("UB200_FUSED_GLU", flag)
+            torch.manual_seed(0)
+            m = _build(P, "llama-3-8b", dtype=dtype, **extra)
+            del emu[:]
+            loss = m(input_ids=ids, labels=ids).loss
+            loss.backward()
+            assert "ub200_gemm_glu" not in emu
+            assert emu.count("ub200_glu_fwd") == 2 and emu.count("ub200_glu_bwd") == 2
+            res[flag] = (loss.detach().float(), _grads(P, m))
+        assert torch.equal(res["1"][0], res["0"][0]) and torch.equal(res["1"][1], res["0"][1])
