@@ -16,6 +16,8 @@
 //   warps 2..5  epilogue: tcgen05.ld accumulator -> registers -> alpha/beta -> global
 //   accumulators are double buffered in TMEM so the epilogue of tile i overlaps the
 //   main loop of tile i+1.
+// EPI = 1 instantiations (ub200_gemm_glu): the same main loop with SIXTEEN epilogue warps (576 threads) that apply
+// the gated activation of LoRA_MLP to the accumulator tile -- see "Gated-activation epilogue" below.
 // Operand layouts: each operand may be K-major (row-major [MN, K]) or MN-major (row-major
 // [K, MN]); MN-major is what makes dX (= dY @ W with W stored [out,in]) and the dA/dB
 // reductions over tokens (X^T @ G) run without any transpose pass.
@@ -168,9 +170,10 @@ __device__ __forceinline__ void store_chunk(const Params& p, const uint32_t (&r)
 //   forward (fast_lora.py:84-87 + swiglu.py:37-47): the tile is g = X @ W_up (+ LoRA); e (the gate
 //     projection, written by the previous launch) is read, g is stored and h = f(e) * g -> C.
 // Same per-element code and rounding points as glu.cu (glu_math.cuh), so both forms give the same bits.
-// One thread owns one row: 32 consecutive columns = 64 contiguous bytes of every tensor per chunk.  The
-// operand loads are issued BEFORE the TMEM read so their latency overlaps it (and the previous chunk's
-// stores); they are evict-first, the operand tiles of the main loop own the L2.
+// One thread owns one row; the unit of work is 16 consecutive columns = ONE 32-byte sector of every tensor
+// (LDG.E.256 / STG.E.256).  The operands of a unit are loaded one unit ahead of their use (two register
+// buffers; across tile boundaries too, see glu_epilogue_tile); loads are evict-first, the operand tiles of
+// the main loop own the L2.  History of the design with measurements: DESIGN.md 4.1c.
 // ---------------------------------------------------------------------------------------
 struct GluRegs {
   uint32_t e[8];      // 16 consecutive 16-bit values of this thread's row (one 32-byte sector)
